@@ -1,0 +1,72 @@
+"""ctypes binding of libtorchrl_b200.so (the C ABI declared in include/torchrl_b200.h).
+
+There is NO fallback: if the shared object is missing or a symbol is absent the import
+of any op raises.  ``load()`` only dlopens the library -- it needs libcudart's static
+copy inside the .so but no GPU, so the symbol/ABI checks run on CPU boxes too.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libtorchrl_b200.so")
+
+c_f32p = ctypes.c_void_p
+c_u8p = ctypes.c_void_p
+c_i32p = ctypes.c_void_p
+c_i64p = ctypes.c_void_p
+c_f64p = ctypes.c_void_p
+vp = ctypes.c_void_p
+i64 = ctypes.c_int64
+i32 = ctypes.c_int
+f32 = ctypes.c_float
+f64 = ctypes.c_double
+u64 = ctypes.c_uint64
+
+# name -> argtypes   (restype is int unless listed in _RESTYPES)
+SIGNATURES = {
+    "trl_last_error": [],
+    "trl_abi_version": [],
+    "trl_device_info": [vp, vp, vp],
+    "trl_gae_scan": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
+    "trl_discount_return": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, vp],
+}
+_RESTYPES = {"trl_last_error": ctypes.c_char_p}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen the library once and type every entry point.  Raises if anything is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            "%s not found: build it with `python -m torchrl_b200.build` (there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise NativeLibraryError("symbol %s missing from %s" % (name, LIB_PATH)) from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    _lib = lib
+    return lib
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = load().trl_last_error()
+        raise RuntimeError("%s failed (rc=%d): %s" % (name, rc, msg.decode() if msg else ""))
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        check(rc, name)
