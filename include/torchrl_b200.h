@@ -45,6 +45,95 @@ int trl_discount_return(const float* rewards, const float* values, const uint8_t
                         int64_t T, int64_t N, float gamma, int time_limit_filter, int variant,
                         void* stream);
 
+/* ---- K1: batched synthetic env (dynamics defined by this build, oracle/synth_env.py) ------------
+ * trl_synth_env_step replaces VecEnv.step / SubProcVecEnv.step (torchrl/env/vecenv.py:53-61,
+ * subproc_vecenv.py:123-140) with the per-env wrapper chain NormAct.action
+ * (env/continuous_wrapper.py:18-20), RewardShift.reward (env/base_wrapper.py:37-41) and
+ * TimeLimitAugment.step (env/base_wrapper.py:152-156) fused in, and accumulates the batch moments
+ * of Normalizer.update_estimate (env/base_wrapper.py:75-82; merged in-kernel when merge_stats=1).
+ * `state` (N,o) is updated in place and IS the raw observation. */
+int trl_synth_env_smem_bytes(int obs_dim, int act_dim);
+int trl_synth_env_num_ctas(int64_t N);
+int trl_synth_env_step(float* state, const float* actions, const float* A, const float* B, const float* c,
+                       const float* lb, const float* ub, int* elapsed, const int* step_count, float* reward,
+                       uint8_t* done, uint8_t* time_limit, double* partial, double* batch_sums,
+                       double* norm_mean, double* norm_var, double* norm_count, unsigned* ticket,
+                       int* any_reset, const int* t_ptr, int64_t N, int obs_dim, int act_dim, float rho,
+                       float eta, float ctrl_cost, float term_thr, float reward_scale, int max_episode_steps,
+                       int max_episode_frames, int merge_stats, void* stream);
+/* VecEnv.reset / partial_reset (env/vecenv.py:42-51): mask NULL = all envs. */
+int trl_synth_env_reset(float* state, int* elapsed, unsigned* episode, const unsigned* seeds,
+                        const uint8_t* mask, int64_t N, int obs_dim, double init_scale, void* stream);
+/* VecEnv.seed (env/vecenv.py:63-65): env i gets seed*n_total + first_env + i. */
+int trl_synth_env_seed(unsigned* seeds, unsigned* episode, int64_t N, unsigned seed, unsigned n_total,
+                       unsigned first_env, void* stream);
+
+/* ---- K2: observation normaliser (env/base_wrapper.py:44-60, 63-94, 103-121) ------------------- */
+int trl_obs_norm_moments(const float* x, int64_t N, int obs_dim, double* sums, void* stream);
+int trl_obs_norm_merge(const double* sums, double batch_n, int obs_dim, double* mean, double* var,
+                       double* count, void* stream);
+int trl_obs_norm_filt(const float* raw, const double* mean, const double* var, int64_t N, int obs_dim,
+                      double clip, float* out, void* stream);
+
+/* ---- K3: tanh-Gaussian action sampling (policies/continuous_policy.py:92-132,
+ * policies/distribution.py:60-76 rsample, :33-45 log_prob).  eps NULL -> in-kernel Philox noise. */
+int trl_tanh_gaussian_sample(const float* mean, const float* log_std, int ls_stride, const float* eps,
+                             float noise_scale, uint64_t seed, const uint64_t* rng_counter, int64_t M,
+                             int act_dim, int tanh_action, float* action, float* pre_tanh, float* log_prob,
+                             float* eps_out, int* nan_flag, void* stream);
+int trl_tanh_gaussian_sample_bwd(const float* action, const float* eps, const float* log_std, int ls_stride,
+                                 const float* g_action, const float* g_logp, int64_t M, int act_dim,
+                                 int tanh_action, float* g_mean, float* g_log_std, void* stream);
+
+/* ---- K4/K5: per-step rollout store + timeout bootstrap + partial reset
+ * (collector/on_policy.py:115-153, collector/base.py:204-228, replay_buffers/base.py:19-37). */
+int trl_collect_finalize(const float* cur_ob_in, const float* next_norm, float* state, const float* act,
+                         const float* value, const float* v_next, const float* reward, const uint8_t* done,
+                         const uint8_t* tl, int* elapsed, unsigned* episode, const unsigned* seeds,
+                         int* step_count, double* ep_return, double* epoch_reward, float* ret_log,
+                         int* n_done, const int* any_reset, const double* norm_mean, const double* norm_var,
+                         float* cur_ob_out, float* b_obs, float* b_next_obs, float* b_acts, float* b_values,
+                         float* b_rewards, uint8_t* b_terminals, uint8_t* b_time_limits, const int* t_ptr,
+                         int64_t N, int obs_dim, int act_dim, int max_episode_frames, float discount,
+                         double init_scale, double clip, int terminal_includes_surpass,
+                         int raw_obs_after_reset, void* stream);
+/* BaseReplayBuffer._advance (replay_buffers/base.py:33-37) on device-side counters. */
+int trl_step_advance(int* t_ptr, int T, int* size_ptr, uint64_t* rng_counter, void* stream);
+
+/* ---- K7/K9/K4: time-row gather / ring write (replay_buffers/on_policy.py:72-91, base.py:19-51).
+ * src/dst/row_bytes are HOST arrays of nkeys entries holding device pointers / byte counts. */
+int trl_row_gather(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                   const int64_t* idx, const int* pos_ptr, int rows, void* stream);
+int trl_ring_write(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                   const int* row_ptr, void* stream);
+/* mean, unbiased std, max, min of a vector (algo/on_policy/ppo.py:141-147). */
+int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream);
+
+/* ---- K8: PPO losses, value + gradient wrt the network outputs (algo/on_policy/ppo.py:41-122). */
+int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim);
+int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
+                       const float* old_logp, const float* advs, const float* adv_stats, int64_t B,
+                       int act_dim, int tanh_action, float clip_para, float entropy_coeff, float* g_mean,
+                       float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
+                       void* stream);
+int trl_ppo_critic_loss(const float* values, const float* returns, const float* old_values, int64_t B,
+                        int clipped, float clip_para, float* g_values, float* info1, double* scratch,
+                        unsigned* ticket, void* stream);
+/* log pi(a|s) of stored actions (policies/continuous_policy.py:134-153). */
+int trl_gaussian_log_prob(const float* mean, const float* log_std, int ls_stride, const float* actions,
+                          int64_t B, int act_dim, int tanh_action, float* logp, void* stream);
+
+/* ---- K11: flat-buffer grad-norm clip + Adam, Polyak (algo/utils.py:16-25, ppo.py:72-74,117-119). */
+int trl_grad_sumsq_blocks(int nseg);
+int trl_grad_sumsq(const float* grad, const int64_t* seg_begin_host, int nseg, unsigned active_mask,
+                   double* sumsq3_out, int* step_counts, double beta1, double beta2, double* scratch,
+                   unsigned* ticket, void* stream);
+int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int64_t* seg_begin_host,
+                  int nseg, unsigned active_mask, const double* sumsq3, const float* lr_dev,
+                  const float* max_norm_host, const float* eps_host, float beta1, float beta2,
+                  float grad_scale, int zero_grad, void* stream);
+int trl_polyak_update(float* target, const float* source, int64_t n, float tau, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,144 @@
+"""K1/K2 parity: device synthetic env vs the NumPy definition (oracle/synth_env.py) and the
+observation normaliser vs the restated reference Normalizer (oracle/ref_numpy.RunningNorm).
+
+The synthetic dynamics have no counterpart in the reference (PARITY UNPINNED by the reference;
+pinned GPU-vs-oracle here).  Resets are bit-exact (integer hash -> 24-bit uniform); a step is fp32
+on the GPU vs float64 in the oracle: rtol 1e-5 / atol 1e-5 per step from identical states.
+"""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as rn
+from oracle import synth_env as oenv
+
+
+def test_spec_constants_agree():
+    from torchrl_b200.env import synth_spec as spec
+    for k in ("RHO", "ETA", "CTRL_COST", "INIT_SCALE", "MAX_EPISODE_STEPS"):
+        assert getattr(spec, k) == getattr(oenv, k)
+    assert spec.SPECS == oenv.SPECS
+    for eid, (o, a, _) in spec.SPECS.items():
+        for x, y in zip(spec.make_params(o, a), oenv.make_params(o, a)):
+            np.testing.assert_array_equal(x, y)
+
+
+def test_oracle_env_through_gym_api():
+    """The CPU env obeys the contract the reference's wrappers rely on (TimeLimit naming, counters)."""
+    from oracle import reference_loader
+    reference_loader.add_shims()
+    import gym
+    env = gym.make("SynthHalfCheetah-v0")
+    assert "TimeLimit" in env.__class__.__name__
+    env.seed(3)
+    ob = env.reset()
+    assert ob.shape == (17,) and np.all(np.abs(ob) <= 0.1)
+    ob2, r, d, info = env.step(np.zeros(6))
+    assert ob2.shape == (17,) and isinstance(r, float) and d is False
+    assert env._elapsed_steps == 1 and env._max_episode_steps == 1000
+    env.seed(3)
+    np.testing.assert_array_equal(env.reset(), ob)       # same (seed, episode 0) -> same state
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env_id,N", [("SynthHalfCheetah-v0", 70), ("SynthAnt-v0", 33)])
+def test_reset_bit_exact_and_step_parity(env_id, N):
+    import torch
+    from torchrl_b200.env import get_vec_env
+    o, a, thr = oenv.SPECS[env_id]
+    env = get_vec_env(env_id, {"reward_scale": 0.5, "obs_norm": False}, N)
+    env.seed(5)
+    ob = env.reset().cpu().numpy()
+    seeds = (5 * N + np.arange(N)) & 0xFFFFFFFF
+    exp = oenv.reset_state(seeds, np.zeros(N), o)
+    np.testing.assert_array_equal(ob, exp.astype(np.float32))          # bit-exact reset
+    A, B, c = oenv.make_params(o, a)
+    rs = np.random.RandomState(0)
+    s = exp.astype(np.float32).astype(np.float64)
+    for t in range(25):
+        act = rs.uniform(-1.3, 1.3, size=(N, a)).astype(np.float32)   # beyond [-1,1] to exercise the clip
+        u = rn.norm_act(act, -np.ones(a), np.ones(a))
+        s2, r, done = oenv.dynamics(s, u, A, B, c, thr)
+        obs, rew, dn, info = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_allclose(obs.cpu().numpy(), s2, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(rew.cpu().numpy()[:, 0], 0.5 * r, rtol=1e-5, atol=1e-5)
+        safe = np.abs(np.abs(s2[:, 1]) - thr) > 1e-4
+        np.testing.assert_array_equal(dn.cpu().numpy()[safe, 0], done[safe])
+        assert not info["time_limit"].any()
+        s = obs.cpu().numpy().astype(np.float64)                        # re-sync: per-step parity
+        # manual partial reset of the done envs, like the collectors do
+        if dn.any():
+            raw = env.partial_reset(dn.squeeze(-1)).cpu().numpy()
+            s = raw.astype(np.float64)
+    assert env.elapsed.max().item() <= 25
+
+
+@pytest.mark.gpu
+def test_time_limit_and_eval_mode():
+    import torch
+    from torchrl_b200.env import SynthVecEnv
+    env = SynthVecEnv("SynthHalfCheetah-v0", 8, {"reward_scale": 3.0, "obs_norm": False}, max_episode_steps=5)
+    env.reset()
+    act = torch.zeros(8, 6, device="cuda")
+    for t in range(5):
+        _, r, d, info = env.step(act)
+        assert bool(d.all()) == (t == 4) and bool(info["time_limit"].all()) == (t == 4)
+    r_train = r.clone()
+    env.reset(); env.eval()
+    for t in range(5):
+        _, r, d, info = env.step(act)
+    # RewardShift only scales in training mode (base_wrapper.py:37-41); second episode differs in state
+    # so compare the scale through a fresh identical episode instead
+    env2 = SynthVecEnv("SynthHalfCheetah-v0", 8, {"reward_scale": 3.0, "obs_norm": False}, max_episode_steps=5)
+    env2.reset(); env2.eval()
+    for t in range(5):
+        _, r2, _, _ = env2.step(act)
+    torch.testing.assert_close(r_train, 3.0 * r2, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_obs_normaliser_matches_reference_formula():
+    """update-then-filter per step, fp64 state, count0=1e-4 (base_wrapper.py:44-121)."""
+    import torch
+    from torchrl_b200.env import get_vec_env
+    N = 100
+    env = get_vec_env("SynthHalfCheetah-v0", {"reward_scale": 1, "obs_norm": True}, N)
+    env.seed(1)
+    ref = rn.RunningNorm(17)
+    raw0 = oenv.reset_state((1 * N + np.arange(N)) & 0xFFFFFFFF, np.zeros(N), 17).astype(np.float32)
+    ob = env.reset().cpu().numpy()
+    ref.update(raw0)
+    np.testing.assert_allclose(ob, ref.filt(raw0), rtol=1e-5, atol=1e-5)
+    rs = np.random.RandomState(1)
+    for t in range(10):
+        act = torch.from_numpy(rs.uniform(-1, 1, size=(N, 6)).astype(np.float32)).cuda()
+        ob, _, _, _ = env.step(act)
+        raw = env.state.cpu().numpy()
+        ref.update(raw)
+        np.testing.assert_allclose(ob.cpu().numpy(), ref.filt(raw), rtol=1e-5, atol=1e-5)
+    nrm = env._obs_normalizer
+    np.testing.assert_allclose(nrm._mean.cpu().numpy(), ref.mean, rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(nrm._var.cpu().numpy(), ref.var, rtol=1e-9, atol=1e-12)
+    assert abs(nrm._count.item() - ref.count) < 1e-9
+    # eval mode: filter only
+    env.eval()
+    ob, _, _, _ = env.step(act)
+    np.testing.assert_allclose(ob.cpu().numpy(), ref.filt(env.state.cpu().numpy()), rtol=1e-5, atol=1e-5)
+    assert abs(nrm._count.item() - ref.count) < 1e-9
+    # pickle round trip (snapshot format)
+    import pickle
+    n2 = pickle.loads(pickle.dumps(nrm))
+    np.testing.assert_array_equal(n2._mean.cpu().numpy(), nrm._mean.cpu().numpy())
+
+
+@pytest.mark.gpu
+def test_sharded_seeding_matches_single_process():
+    """rank g of G owns envs [g*N/G, (g+1)*N/G): the union equals the single-process env set."""
+    import torch
+    from torchrl_b200.env import SynthVecEnv
+    full = SynthVecEnv("SynthHalfCheetah-v0", 64, {"obs_norm": False})
+    full.seed(7)
+    ref = full.reset().clone()
+    for g in range(4):
+        part = SynthVecEnv("SynthHalfCheetah-v0", 16, {"obs_norm": False}, first_env=16 * g, total_envs=64)
+        part.seed(7)
+        torch.testing.assert_close(part.reset(), ref[16 * g:16 * (g + 1)], rtol=0, atol=0)

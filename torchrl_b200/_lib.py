@@ -21,6 +21,7 @@ i32 = ctypes.c_int
 f32 = ctypes.c_float
 f64 = ctypes.c_double
 u64 = ctypes.c_uint64
+u32 = ctypes.c_uint32
 
 # name -> argtypes   (restype is int unless listed in _RESTYPES)
 SIGNATURES = {
@@ -29,8 +30,34 @@ SIGNATURES = {
     "trl_device_info": [vp, vp, vp],
     "trl_gae_scan": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, f32, i32, i32, vp],
     "trl_discount_return": [vp, vp, vp, vp, vp, vp, vp, i64, i64, f32, i32, i32, vp],
+    "trl_synth_env_smem_bytes": [i32, i32],
+    "trl_synth_env_num_ctas": [i64],
+    "trl_synth_env_step": [vp] * 20 + [i64, i32, i32, f32, f32, f32, f32, f32, i32, i32, i32, vp],
+    "trl_synth_env_reset": [vp, vp, vp, vp, vp, i64, i32, f64, vp],
+    "trl_synth_env_seed": [vp, vp, i64, u32, u32, u32, vp],
+    "trl_obs_norm_moments": [vp, i64, i32, vp, vp],
+    "trl_obs_norm_merge": [vp, f64, i32, vp, vp, vp, vp],
+    "trl_obs_norm_filt": [vp, vp, vp, i64, i32, f64, vp, vp],
+    "trl_tanh_gaussian_sample": [vp, vp, i32, vp, f32, u64, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp],
+    "trl_tanh_gaussian_sample_bwd": [vp, vp, vp, i32, vp, vp, i64, i32, i32, vp, vp, vp],
+    "trl_collect_finalize": [vp] * 29 + [i64, i32, i32, i32, f32, f64, f64, i32, i32, vp],
+    "trl_step_advance": [vp, i32, vp, vp, vp],
+    "trl_row_gather": [i32, vp, vp, vp, vp, vp, i32, vp],
+    "trl_ring_write": [i32, vp, vp, vp, vp, vp],
+    "trl_vec_stats": [vp, i64, vp, vp],
+    "trl_ppo_actor_scratch_doubles": [i64, i32],
+    "trl_ppo_actor_loss": [vp, vp, i32, vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
+    "trl_ppo_critic_loss": [vp, vp, vp, i64, i32, f32, vp, vp, vp, vp, vp],
+    "trl_gaussian_log_prob": [vp, vp, i32, vp, i64, i32, i32, vp, vp],
+    "trl_grad_sumsq_blocks": [i32],
+    "trl_grad_sumsq": [vp, vp, i32, u32, vp, vp, f64, f64, vp, vp, vp],
+    "trl_adam_step": [vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp, f32, f32, f32, i32, vp],
+    "trl_polyak_update": [vp, vp, i64, f32, vp],
 }
-_RESTYPES = {"trl_last_error": ctypes.c_char_p}
+_RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles": ctypes.c_int64}
+# entry points that return a value rather than an error code
+_VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas",
+                "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")
 
 _lib = None
 

@@ -1,0 +1,2 @@
+from .base import BaseCollector, VecCollector  # noqa: F401
+from .on_policy import OnPolicyCollectorBase, VecOnPolicyCollector  # noqa: F401

@@ -1,0 +1,149 @@
+// gather.cu -- K7 / K9 / K4: time-row gather (minibatch assembly), ring write, advantage statistics.
+//
+// Replaces
+//   OnPolicyReplayBufferBase.one_iteration  /root/reference/torchrl/replay_buffers/on_policy.py:72-91
+//   BaseReplayBuffer.random_batch           /root/reference/torchrl/replay_buffers/base.py:39-51
+//   BaseReplayBuffer.add_sample/_advance    /root/reference/torchrl/replay_buffers/base.py:19-37
+//   advantage statistics / normalisation    /root/reference/torchrl/algo/on_policy/ppo.py:141-147
+// Sampling granularity is the TIME ROW: a sampled index selects one
+// contiguous (N, D) slab, so "gather" is b contiguous memcpys per key; all keys of a
+// minibatch are moved by ONE launch (grid.y = key).  The row indices themselves are produced
+// by the host with the reference's own NumPy calls (bit-exact replay indexing) and uploaded.
+// HBM-bound: 2 x row_bytes per (row, key).
+#include "common.cuh"
+
+namespace trl {
+
+constexpr int kMaxKeys = 8;
+
+struct RowCopyParams {
+  const char* src[kMaxKeys];
+  char* dst[kMaxKeys];
+  long long row_bytes[kMaxKeys];   // N * D * elemsize
+  int nkeys;
+  const long long* idx;            // row indices (device) or nullptr
+  const int* pos_ptr;              // optional device scalar: use idx[(*pos_ptr)*rows + k]
+  const int* row_ptr;              // optional device scalar: single row index (ring write at *row_ptr)
+  int rows;                        // number of rows moved
+  int scatter;                     // 0: dst[k] = src[idx[k]] ; 1: dst[idx[k]] = src[k]
+  long long src_rows;              // rows in the gather source (bounds check), 0 = unchecked
+};
+
+template <typename V>
+__device__ __forceinline__ void copy_units(const char* s, char* d, long long nbytes, int tid, int nthr) {
+  const V* sv = reinterpret_cast<const V*>(s);
+  V* dv = reinterpret_cast<V*>(d);
+  const long long n = nbytes / static_cast<long long>(sizeof(V));
+  for (long long i = tid; i < n; i += nthr) dv[i] = sv[i];
+}
+
+// grid = (chunks_per_row, rows, nkeys); each CTA copies one chunk of one row of one key
+__global__ void __launch_bounds__(256) row_copy_kernel(const RowCopyParams p) {
+  const int key = blockIdx.z, k = blockIdx.y;
+  long long r;
+  if (p.row_ptr) r = *p.row_ptr;
+  else if (p.idx) r = p.idx[(p.pos_ptr ? static_cast<long long>(*p.pos_ptr) * p.rows : 0) + k];
+  else r = k;
+  const long long rb = p.row_bytes[key];
+  const long long srow = p.scatter ? k : r, drow = p.scatter ? r : k;
+  const char* s = p.src[key] + srow * rb;
+  char* d = p.dst[key] + drow * rb;
+  // chunking: split the row over gridDim.x CTAs in 16B-aligned pieces
+  long long per = ceil_div<long long>(rb, gridDim.x);
+  per = (per + 15) & ~15LL;
+  const long long lo = per * blockIdx.x;
+  if (lo >= rb) return;
+  const long long len = min(per, rb - lo);
+  s += lo; d += lo;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(len);
+  if ((al & 15) == 0) copy_units<uint4>(s, d, len, threadIdx.x, blockDim.x);
+  else if ((al & 3) == 0) copy_units<unsigned>(s, d, len, threadIdx.x, blockDim.x);
+  else copy_units<unsigned char>(s, d, len, threadIdx.x, blockDim.x);
+}
+
+// stats[0..3] = mean, unbiased std, max, min of x[0..n)   (one CTA; fp64 accumulation)
+__global__ void __launch_bounds__(1024) vec_stats_kernel(const float* __restrict__ x, long long n,
+                                                        float* __restrict__ stats) {
+  __shared__ double sh_s[32], sh_q[32];
+  __shared__ float sh_mx[32], sh_mn[32];
+  double s = 0.0, q = 0.0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    s += v; q += static_cast<double>(v) * v;
+    mx = fmaxf(mx, v); mn = fminf(mn, v);
+  }
+  s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sh_s[wid] = s; sh_q[wid] = q; sh_mx[wid] = mx; sh_mn[wid] = mn; }
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < nw ? sh_s[lane] : 0.0; q = lane < nw ? sh_q[lane] : 0.0;
+    mx = lane < nw ? sh_mx[lane] : -INFINITY; mn = lane < nw ? sh_mn[lane] : INFINITY;
+    s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+    if (lane == 0) {
+      const double dn = static_cast<double>(n);
+      const double mean = s / dn;
+      double var = (q - s * mean) / (dn - 1.0);   // unbiased (torch.std default); n==1 -> nan like torch
+      if (var < 0.0) var = 0.0;
+      stats[0] = static_cast<float>(mean);
+      stats[1] = static_cast<float>(sqrt(var));
+      stats[2] = mx;
+      stats[3] = mn;
+    }
+  }
+}
+
+}  // namespace trl
+
+static int launch_row_copy(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                           const int64_t* idx, const int* pos_ptr, const int* row_ptr, int rows, int scatter,
+                           void* stream, const char* who) {
+  using namespace trl;
+  TRL_REQUIRE(nkeys >= 1 && nkeys <= kMaxKeys, "%s: nkeys %d not in 1..%d", who, nkeys, kMaxKeys);
+  TRL_REQUIRE(rows >= 0, "%s: negative row count", who);
+  if (rows == 0) return TRL_OK;
+  TRL_REQUIRE(src && dst && row_bytes, "%s: null key table", who);
+  RowCopyParams p;
+  long long max_rb = 0;
+  for (int i = 0; i < nkeys; ++i) {
+    TRL_REQUIRE(src[i] && dst[i] && row_bytes[i] > 0, "%s: key %d has a null pointer or empty row", who, i);
+    p.src[i] = static_cast<const char*>(src[i]);
+    p.dst[i] = static_cast<char*>(dst[i]);
+    p.row_bytes[i] = row_bytes[i];
+    max_rb = max_rb > row_bytes[i] ? max_rb : row_bytes[i];
+  }
+  p.nkeys = nkeys;
+  p.idx = reinterpret_cast<const long long*>(idx);
+  p.pos_ptr = pos_ptr;
+  p.row_ptr = row_ptr;
+  p.rows = rows;
+  p.scatter = scatter;
+  p.src_rows = 0;
+  // ~16 KB per CTA, but never more CTAs than ~8 waves of the chip
+  long long chunks = ceil_div<long long>(max_rb, 16384);
+  const long long cap = ceil_div<long long>(8LL * kNumSM, static_cast<long long>(rows) * nkeys);
+  if (chunks > cap) chunks = cap < 1 ? 1 : cap;
+  row_copy_kernel<<<dim3(static_cast<unsigned>(chunks), rows, nkeys), 256, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("row_copy_kernel");
+}
+
+TRL_API int trl_row_gather(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                           const int64_t* idx, const int* pos_ptr, int rows, void* stream) {
+  TRL_REQUIRE(idx, "trl_row_gather: null index pointer");
+  return launch_row_copy(nkeys, src, dst, row_bytes, idx, pos_ptr, nullptr, rows, 0, stream, "trl_row_gather");
+}
+
+TRL_API int trl_ring_write(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                           const int* row_ptr, void* stream) {
+  TRL_REQUIRE(row_ptr, "trl_ring_write: null row pointer");
+  return launch_row_copy(nkeys, src, dst, row_bytes, nullptr, nullptr, row_ptr, 1, 1, stream, "trl_ring_write");
+}
+
+TRL_API int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(n >= 1, "trl_vec_stats: need at least one element");
+  TRL_REQUIRE(x && stats4, "trl_vec_stats: null pointer");
+  vec_stats_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n, stats4);
+  return check_launch("vec_stats_kernel");
+}

@@ -1,0 +1,111 @@
+"""Flat parameter / gradient buffers and the fused multi-segment Adam (K11, csrc/optim.cu).
+
+A *segment* is the parameter set of one optimizer of the reference (e.g. PPO: pf and vf,
+/root/reference/torchrl/algo/on_policy/a2c.py:29-39).  All segments live in one contiguous fp32
+buffer; ``nn.Parameter.data`` and ``.grad`` become views into it, so
+  * global-norm clipping + Adam + zero_grad is two launches for the whole agent,
+  * the multi-GPU path all-reduces ONE tensor (K12).
+"""
+import ctypes
+
+import torch
+
+from . import _lib, ops
+
+F32, F64, I32 = torch.float32, torch.float64, torch.int32
+
+
+def _params_of(seg):
+    if isinstance(seg, torch.nn.Module):
+        return [p for p in seg.parameters()]
+    return list(seg)
+
+
+class FlatParams:
+    """Re-home the parameters of several segments into one flat buffer (data only)."""
+
+    def __init__(self, segments, device=None):
+        self.segments = [_params_of(s) for s in segments]
+        plist = [p for seg in self.segments for p in seg]
+        assert plist, "no parameters"
+        self.device = torch.device(device) if device is not None else plist[0].device
+        sizes = [sum(p.numel() for p in seg) for seg in self.segments]
+        self.seg_begin = [0]
+        for s in sizes:
+            self.seg_begin.append(self.seg_begin[-1] + s)
+        self.total = self.seg_begin[-1]
+        self.data = torch.empty(self.total, dtype=F32, device=self.device)
+        off = 0
+        for p in plist:
+            n = p.numel()
+            self.data[off:off + n].copy_(p.data.reshape(-1))
+            p.data = self.data[off:off + n].view(p.shape)
+            off += n
+        self.params = plist
+
+    def seg_slice(self, i, j=None):
+        j = i + 1 if j is None else j
+        return self.data[self.seg_begin[i]:self.seg_begin[j]]
+
+
+class FlatAdam(FlatParams):
+    """Adam over flat segments with per-segment lr / eps / max-norm, matching torch.optim.Adam +
+    torch.nn.utils.clip_grad_norm_ applied per segment (the reference's per-network optimizers)."""
+
+    def __init__(self, segments, lrs, eps=1e-8, max_norms=None, betas=(0.9, 0.999), device=None):
+        super().__init__(segments, device)
+        n = len(self.segments)
+        assert n <= 8
+        self.nseg = n
+        self.grad = torch.zeros(self.total, dtype=F32, device=self.device)
+        self.exp_avg = torch.zeros(self.total, dtype=F32, device=self.device)
+        self.exp_avg_sq = torch.zeros(self.total, dtype=F32, device=self.device)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+        lrs = [float(x) for x in (lrs if isinstance(lrs, (list, tuple)) else [lrs] * n)]
+        eps = [float(x) for x in (eps if isinstance(eps, (list, tuple)) else [eps] * n)]
+        if max_norms is None:
+            max_norms = [0.0] * n
+        max_norms = [0.0 if m is None else float(m) for m in (max_norms if isinstance(max_norms, (list, tuple))
+                                                              else [max_norms] * n)]
+        self.lr_host = torch.tensor(lrs, dtype=F32).pin_memory() if torch.cuda.is_available() else torch.tensor(lrs)
+        self.lr = self.lr_host.to(self.device)
+        self.initial_lrs = list(lrs)
+        self.betas = (float(betas[0]), float(betas[1]))
+        self.step_counts = torch.zeros(n, dtype=I32, device=self.device)
+        self.sumsq3 = torch.zeros(3 * n, dtype=F64, device=self.device)
+        nb = int(_lib.load().trl_grad_sumsq_blocks(n))
+        self._scratch = torch.zeros(nb, dtype=F64, device=self.device)
+        self._ticket = torch.zeros(1, dtype=I32, device=self.device)
+        self._seg_c = (ctypes.c_int64 * (n + 1))(*self.seg_begin)
+        self._max_norm_c = (ctypes.c_float * n)(*max_norms)
+        self._eps_c = (ctypes.c_float * n)(*eps)
+        self.all_mask = (1 << n) - 1
+
+    def set_lr(self, seg, lr):
+        """Host-side LR schedule (update_linear_schedule, /root/reference/torchrl/algo/utils.py:28-32):
+        the value goes to a device scalar so captured graphs pick it up without re-capture."""
+        self.lr_host[seg] = float(lr)
+        self.lr.copy_(self.lr_host, non_blocking=True)
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def step(self, active_mask=None, grad_scale=1.0, zero_grad=True):
+        """clip (per segment, global norm) + Adam + zero the gradient: two launches."""
+        mask = self.all_mask if active_mask is None else int(active_mask)
+        st = ops._stream()
+        _lib.call("trl_grad_sumsq", self.grad.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
+                  self.step_counts.data_ptr(), self.betas[0], self.betas[1], self._scratch.data_ptr(),
+                  self._ticket.data_ptr(), st)
+        _lib.call("trl_adam_step", self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+                  self.exp_avg_sq.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
+                  self.lr.data_ptr(), self._max_norm_c, self._eps_c, self.betas[0], self.betas[1],
+                  float(grad_scale), int(bool(zero_grad)), st)
+
+    def grad_norms(self):
+        """Pre-clip total norm per segment of the last step (what clip_grad_norm_ returns)."""
+        return torch.sqrt(self.sumsq3[:self.nseg])

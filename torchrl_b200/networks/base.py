@@ -1,0 +1,92 @@
+"""Feature trunks: MLPBase and CNNBase (API of /root/reference/torchrl/networks/base.py:8-107).
+
+Plain ``nn.Module``s -- the north star keeps the small policy/value nets in PyTorch (cuBLAS);
+everything around them is in the CUDA library.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import init as winit
+
+
+class MLPBase(nn.Module):
+    """Linear -> act, repeated; the last hidden layer keeps an activation too
+    (`last_activation_func`, defaulting to `activation_func`; base.py:24-41)."""
+
+    def __init__(self, input_shape, hidden_shapes, activation_func=nn.ReLU, init_func=winit.basic_init,
+                 add_ln=False, last_activation_func=None):
+        super().__init__()
+        self.activation_func = activation_func
+        self.add_ln = add_ln
+        self.last_activation_func = last_activation_func if last_activation_func is not None else activation_func
+        width = int(np.prod(input_shape))
+        self.output_shape = width
+        layers = []
+        for i, h in enumerate(hidden_shapes):
+            fc = nn.Linear(width, h)
+            init_func(fc)
+            layers.append(fc)
+            last = (i == len(hidden_shapes) - 1)
+            if last and not add_ln:
+                layers.append(self.last_activation_func())
+            else:
+                layers.append(activation_func())
+                if add_ln:
+                    layers.append(nn.LayerNorm(h))
+            width = h
+            self.output_shape = h
+        if add_ln and layers:
+            # reference quirk (base.py:39-40): the trailing LayerNorm is dropped and replaced by
+            # the last activation
+            layers.pop(-1)
+            layers.append(self.last_activation_func())
+        self.fcs = layers
+        self.seq_fcs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        return self.seq_fcs(x)
+
+
+def calc_next_shape(input_shape, conv_info):
+    out_channels, kernel_size, stride, padding = conv_info
+    _, h, w = input_shape
+    h = int((h + 2 * padding[0] - (kernel_size[0] - 1) - 1) / stride[0] + 1)
+    w = int((w + 2 * padding[1] - (kernel_size[1] - 1) - 1) / stride[1] + 1)
+    return (out_channels, h, w)
+
+
+class CNNBase(nn.Module):
+    """Conv stack over (..., C, H, W) inputs flattened to (..., features) (base.py:59-107)."""
+
+    def __init__(self, input_shape, hidden_shapes, activation_func=nn.ReLU, init_func=winit.basic_init,
+                 add_ln=False, last_activation_func=None):
+        super().__init__()
+        self.add_ln = add_ln
+        self.activation_func = activation_func
+        self.last_activation_func = last_activation_func if last_activation_func is not None else activation_func
+        shape = tuple(input_shape)
+        channels = shape[0]
+        self.output_shape = shape[0] * shape[1] * shape[2]
+        layers = []
+        for info in hidden_shapes:
+            out_c, k, s, p = info
+            conv = nn.Conv2d(channels, out_c, tuple(k), tuple(s), tuple(p))
+            init_func(conv)
+            layers.append(conv)
+            layers.append(activation_func())
+            channels = out_c
+            shape = calc_next_shape(shape, info)
+            if add_ln:
+                layers.append(nn.LayerNorm(shape[1:]))
+            self.output_shape = shape[0] * shape[1] * shape[2]
+        if layers:
+            layers.pop(-1)
+            layers.append(self.last_activation_func())
+        self.convs = layers
+        self.seq_convs = nn.Sequential(*layers)
+
+    def forward(self, x):
+        lead = x.shape[:-3]
+        out = self.seq_convs(x.reshape((-1,) + tuple(x.shape[-3:])))
+        return out.reshape(tuple(lead) + (-1,))

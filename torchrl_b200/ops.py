@@ -1,12 +1,17 @@
 """Tensor-level wrappers over the C ABI (include/torchrl_b200.h).
 
 Each function takes torch CUDA tensors, checks dtype / contiguity / device, and launches
-the sm_100a kernel on torch's *current* stream (so the calls are CUDA-graph capturable).
-Memory is owned by PyTorch's caching allocator; the library never allocates.
+the sm_100a kernel on torch's *current* stream (so every call is CUDA-graph capturable).
+Memory is owned by PyTorch's caching allocator; the library never allocates.  There is no
+CPU implementation: CPU tensors raise.
 """
+import ctypes
+
 import torch
 
 from . import _lib
+
+F32, F64, U8, I32, I64 = torch.float32, torch.float64, torch.uint8, torch.int32, torch.int64
 
 
 def _stream():
@@ -23,6 +28,10 @@ def _chk(t, dtype, name):
     return t.data_ptr()
 
 
+def _opt(t, dtype, name):
+    return None if t is None else _chk(t, dtype, name)
+
+
 def _tn(t):
     """(T, N) sizes of a (T,N) or (T,N,1) tensor."""
     if t.dim() == 3 and t.shape[2] == 1:
@@ -32,9 +41,10 @@ def _tn(t):
     raise ValueError("expected a (T,N) or (T,N,1) tensor, got %s" % (tuple(t.shape),))
 
 
+# ------------------------------------------------------------------------------------------ K6
 def gae_scan(rewards, values, terminals, time_limits, last_value, gamma, tau, time_limit_filter,
              advs=None, returns=None, variant=1):
-    """GAE backward scan (K6).  Mirrors OnPolicyReplayBufferBase.generalized_advantage_estimation
+    """GAE backward scan.  Mirrors OnPolicyReplayBufferBase.generalized_advantage_estimation
     (/root/reference/torchrl/replay_buffers/on_policy.py:16-44) on (T,N[,1]) device tensors."""
     T, N = _tn(rewards)
     if advs is None:
@@ -44,17 +54,16 @@ def gae_scan(rewards, values, terminals, time_limits, last_value, gamma, tau, ti
     assert values.shape == rewards.shape and terminals.shape == rewards.shape and \
         time_limits.shape == rewards.shape and last_value.numel() == N
     _lib.call("trl_gae_scan",
-              _chk(rewards, torch.float32, "rewards"), _chk(values, torch.float32, "values"),
-              _chk(terminals, torch.uint8, "terminals"), _chk(time_limits, torch.uint8, "time_limits"),
-              _chk(last_value, torch.float32, "last_value"),
-              _chk(advs, torch.float32, "advs"), _chk(returns, torch.float32, "returns"),
+              _chk(rewards, F32, "rewards"), _chk(values, F32, "values"),
+              _chk(terminals, U8, "terminals"), _chk(time_limits, U8, "time_limits"),
+              _chk(last_value, F32, "last_value"), _chk(advs, F32, "advs"), _chk(returns, F32, "returns"),
               T, N, float(gamma), float(tau), int(bool(time_limit_filter)), int(variant), _stream())
     return advs, returns
 
 
 def discount_return(rewards, values, terminals, time_limits, last_value, gamma, time_limit_filter,
                     advs=None, returns=None, variant=1):
-    """Discounted-reward returns (K6).  Mirrors OnPolicyReplayBufferBase.discount_reward
+    """Discounted-reward returns.  Mirrors OnPolicyReplayBufferBase.discount_reward
     (/root/reference/torchrl/replay_buffers/on_policy.py:46-70)."""
     T, N = _tn(rewards)
     if advs is None:
@@ -63,9 +72,188 @@ def discount_return(rewards, values, terminals, time_limits, last_value, gamma, 
         returns = torch.empty_like(rewards)
     assert values.shape == rewards.shape and last_value.numel() == N
     _lib.call("trl_discount_return",
-              _chk(rewards, torch.float32, "rewards"), _chk(values, torch.float32, "values"),
-              _chk(terminals, torch.uint8, "terminals"), _chk(time_limits, torch.uint8, "time_limits"),
-              _chk(last_value, torch.float32, "last_value"),
-              _chk(advs, torch.float32, "advs"), _chk(returns, torch.float32, "returns"),
+              _chk(rewards, F32, "rewards"), _chk(values, F32, "values"),
+              _chk(terminals, U8, "terminals"), _chk(time_limits, U8, "time_limits"),
+              _chk(last_value, F32, "last_value"), _chk(advs, F32, "advs"), _chk(returns, F32, "returns"),
               T, N, float(gamma), int(bool(time_limit_filter)), int(variant), _stream())
     return advs, returns
+
+
+# ------------------------------------------------------------------------------------------ K2
+def obs_norm_moments(x, sums=None):
+    N, o = x.shape
+    if sums is None:
+        sums = torch.empty(2 * o, dtype=F64, device=x.device)
+    _lib.call("trl_obs_norm_moments", _chk(x, F32, "x"), N, o, _chk(sums, F64, "sums"), _stream())
+    return sums
+
+
+def obs_norm_merge(sums, batch_n, mean, var, count):
+    o = mean.numel()
+    _lib.call("trl_obs_norm_merge", _chk(sums, F64, "sums"), float(batch_n), o, _chk(mean, F64, "mean"),
+              _chk(var, F64, "var"), _chk(count, F64, "count"), _stream())
+
+
+def obs_norm_filt(raw, mean, var, clip=10.0, out=None):
+    N, o = raw.shape
+    if out is None:
+        out = torch.empty_like(raw)
+    _lib.call("trl_obs_norm_filt", _chk(raw, F32, "raw"), _chk(mean, F64, "mean"), _chk(var, F64, "var"), N, o,
+              float(clip), _chk(out, F32, "out"), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K3
+def tanh_gaussian_sample(mean, log_std, eps=None, tanh_action=True, want_log_prob=False, want_pre_tanh=False,
+                         want_eps=False, noise_scale=1.0, rng=None, nan_flag=None, action_out=None):
+    """action = tanh(mean + exp(log_std)*eps) (+ log-prob, pre-tanh).  eps None -> Philox noise keyed by
+    (rng.seed, rng.counter).  Mirrors TanhNormal.rsample / log_prob
+    (/root/reference/torchrl/policies/distribution.py:60-76, 33-45)."""
+    a = mean.shape[-1]
+    M = mean.numel() // a
+    action = action_out if action_out is not None else torch.empty_like(mean)
+    pre = torch.empty_like(mean) if want_pre_tanh else None
+    logp = torch.empty(mean.shape[:-1] + (1,), dtype=F32, device=mean.device) if want_log_prob else None
+    eps_out = torch.empty_like(mean) if want_eps else None
+    ls_stride = 0 if log_std.dim() == 1 else a
+    if ls_stride:
+        assert log_std.shape == mean.shape
+    seed, ctr = (0, None)
+    if eps is None:
+        if rng is None or rng.counter is None:
+            raise ValueError("tanh_gaussian_sample needs either eps or an rng state")
+        seed, ctr = rng.seed, rng.counter
+    _lib.call("trl_tanh_gaussian_sample", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
+              _opt(eps, F32, "eps"), float(noise_scale), ctypes.c_uint64(seed), _opt(ctr, I64, "rng_counter"), M, a,
+              int(bool(tanh_action)), _chk(action, F32, "action"), _opt(pre, F32, "pre_tanh"),
+              _opt(logp, F32, "log_prob"), _opt(eps_out, F32, "eps_out"), _opt(nan_flag, I32, "nan_flag"), _stream())
+    out = {"action": action}
+    if pre is not None:
+        out["pre_tanh"] = pre
+    if logp is not None:
+        out["log_prob"] = logp
+    if eps_out is not None:
+        out["eps"] = eps_out
+    return out
+
+
+def tanh_gaussian_sample_bwd(action, eps, log_std, g_action, g_logp, tanh_action):
+    a = action.shape[-1]
+    M = action.numel() // a
+    g_mean = torch.empty_like(action)
+    g_ls = torch.empty_like(action)
+    ls_stride = 0 if log_std.dim() == 1 else a
+    ga = g_action.contiguous() if g_action is not None else None
+    gl = g_logp.contiguous() if g_logp is not None else None
+    _lib.call("trl_tanh_gaussian_sample_bwd", _chk(action, F32, "action"), _chk(eps, F32, "eps"),
+              _chk(log_std, F32, "log_std"), ls_stride, _opt(ga, F32, "g_action"), _opt(gl, F32, "g_logp"), M, a,
+              int(bool(tanh_action)), _chk(g_mean, F32, "g_mean"), _chk(g_ls, F32, "g_log_std"), _stream())
+    return g_mean, g_ls
+
+
+def counter_advance(counter, t_ptr=None, T=1, size_ptr=None):
+    """Device-side `counter += 1` (and optionally t = (t+1) % T, size = min(size+1, T))."""
+    _lib.call("trl_step_advance", _opt(t_ptr, I32, "t_ptr"), int(T), _opt(size_ptr, I32, "size_ptr"),
+              _opt(counter, I64, "counter"), _stream())
+
+
+# ------------------------------------------------------------------------------------------ K7/K9/K4
+class RowCopyPlan:
+    """Pre-built key table for trl_row_gather / trl_ring_write (host arrays of device pointers)."""
+
+    def __init__(self, srcs, dsts, row_bytes):
+        n = len(srcs)
+        assert n == len(dsts) == len(row_bytes) and 1 <= n <= 8
+        self.n = n
+        self.src = (ctypes.c_void_p * n)(*[s.data_ptr() for s in srcs])
+        self.dst = (ctypes.c_void_p * n)(*[d.data_ptr() for d in dsts])
+        self.rb = (ctypes.c_int64 * n)(*[int(b) for b in row_bytes])
+        self._keep = (list(srcs), list(dsts))
+
+
+def row_bytes_of(t):
+    """bytes of one time-row of a (T, N, ...) tensor"""
+    return t[0].numel() * t.element_size()
+
+
+def row_gather(plan, idx, rows, pos_ptr=None):
+    """dst[k] = src[idx[pos*rows + k]] for every key of the plan; idx is an int64 device tensor."""
+    _lib.call("trl_row_gather", plan.n, plan.src, plan.dst, plan.rb, _chk(idx, I64, "idx"),
+              _opt(pos_ptr, I32, "pos_ptr"), int(rows), _stream())
+
+
+def ring_write(plan, row_ptr):
+    """dst[*row_ptr] = src[0] for every key of the plan (one time-row)."""
+    _lib.call("trl_ring_write", plan.n, plan.src, plan.dst, plan.rb, _chk(row_ptr, I32, "row_ptr"), _stream())
+
+
+def vec_stats(x, out=None):
+    """[mean, unbiased std, max, min] of a float vector, on the device."""
+    if out is None:
+        out = torch.empty(4, dtype=F32, device=x.device)
+    _lib.call("trl_vec_stats", _chk(x, F32, "x"), x.numel(), _chk(out, F32, "stats"), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K8
+class LossScratch:
+    """Scratch + ticket for the two-level reductions of the loss kernels (allocated once)."""
+
+    def __init__(self, B, act_dim, device):
+        n = int(_lib.load().trl_ppo_actor_scratch_doubles(int(B), int(act_dim)))
+        self.actor = torch.zeros(max(n, 1), dtype=F64, device=device)
+        self.critic = torch.zeros(max((int(B) + 255) // 256, 1), dtype=F64, device=device)
+        self.tickets = torch.zeros(4, dtype=I32, device=device)
+        self.B, self.a = int(B), int(act_dim)
+
+
+def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para, entropy_coeff, tanh_action,
+                   scratch, g_mean=None, g_log_std=None, info=None, logp_out=None):
+    """PPO clipped-surrogate loss value, dL/dmean, dL/dlog_std and logged stats in one launch
+    (/root/reference/torchrl/algo/on_policy/ppo.py:41-91)."""
+    B, a = mean.shape
+    assert scratch.B >= B and scratch.a == a
+    ls_stride = 0 if log_std.dim() == 1 else a
+    if g_mean is None:
+        g_mean = torch.empty_like(mean)
+    if g_log_std is None:
+        g_log_std = torch.empty_like(log_std)
+    if info is None:
+        info = torch.zeros(16, dtype=F32, device=mean.device)
+    _lib.call("trl_ppo_actor_loss", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
+              _chk(actions, F32, "actions"), _chk(old_logp, F32, "old_logp"), _chk(advs, F32, "advs"),
+              _opt(adv_stats, F32, "adv_stats"), B, a, int(bool(tanh_action)), float(clip_para),
+              float(entropy_coeff), _chk(g_mean, F32, "g_mean"), _chk(g_log_std, F32, "g_log_std"),
+              _opt(logp_out, F32, "logp_out"), _chk(info, F32, "info"), _chk(scratch.actor, F64, "scratch"),
+              scratch.tickets[0:1].data_ptr(), _stream())
+    return g_mean, g_log_std, info
+
+
+def ppo_critic_loss(values, returns, old_values, clipped, clip_para, scratch, g_values=None, info=None):
+    """Critic loss value and dL/dV (/root/reference/torchrl/algo/on_policy/ppo.py:93-122)."""
+    B = values.numel()
+    if g_values is None:
+        g_values = torch.empty_like(values)
+    if info is None:
+        info = torch.zeros(1, dtype=F32, device=values.device)
+    _lib.call("trl_ppo_critic_loss", _chk(values, F32, "values"), _chk(returns, F32, "returns"),
+              _opt(old_values, F32, "old_values"), B, int(bool(clipped)), float(clip_para),
+              _chk(g_values, F32, "g_values"), _chk(info, F32, "info"), _chk(scratch.critic, F64, "scratch"),
+              scratch.tickets[1:2].data_ptr(), _stream())
+    return g_values, info
+
+
+def gaussian_log_prob(mean, log_std, actions, tanh_action, out=None):
+    B, a = mean.shape
+    if out is None:
+        out = torch.empty(B, dtype=F32, device=mean.device)
+    ls_stride = 0 if log_std.dim() == 1 else a
+    _lib.call("trl_gaussian_log_prob", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
+              _chk(actions, F32, "actions"), B, a, int(bool(tanh_action)), _chk(out, F32, "logp"), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------ K11
+def polyak_update(target_flat, source_flat, tau):
+    _lib.call("trl_polyak_update", _chk(target_flat, F32, "target"), _chk(source_flat, F32, "source"),
+              target_flat.numel(), float(tau), _stream())

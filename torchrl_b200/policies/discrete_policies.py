@@ -1,0 +1,114 @@
+"""Discrete-action policies (API of /root/reference/torchrl/policies/discrete_policies.py).
+
+Differences from the reference, all documented in SURVEY.md Appendix A: the QR-DQN policy's
+`q_to_a` works for any number of envs (the reference calls .item(), A.5) and epsilon-greedy
+draws stay on the device unless the noise mode is "reference_cpu" (then np.random is used in
+the reference's call order).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.distributions import Categorical
+
+from .. import networks
+from . import distribution as D
+
+
+class UniformPolicyDiscrete(nn.Module):
+    def __init__(self, action_num):
+        super().__init__()
+        self.action_num = action_num
+        self.continuous = False
+
+    def forward(self, x):
+        return np.random.randint(self.action_num)
+
+    def explore(self, x):
+        return {"action": np.random.randint(self.action_num)}
+
+
+class EpsilonGreedyDQNDiscretePolicy:
+    """epsilon-greedy wrapper over a Q network (discrete_policies.py:25-74)."""
+
+    def __init__(self, qf, start_epsilon, end_epsilon, decay_frames, action_shape):
+        self.qf = qf
+        self.start_epsilon = start_epsilon
+        self.end_epsilon = end_epsilon
+        self.decay_frames = decay_frames
+        self.count = 0
+        self.action_shape = action_shape
+        self.epsilon = self.start_epsilon
+        self.continuous = False
+
+    def q_to_a(self, q):
+        return q.max(dim=-1, keepdim=True)[1].detach()
+
+    def _anneal(self):
+        self.count += 1
+        if self.count < self.decay_frames:
+            self.epsilon = self.start_epsilon - (self.start_epsilon - self.end_epsilon) * (self.count / self.decay_frames)
+        else:
+            self.epsilon = self.end_epsilon
+
+    def explore(self, x):
+        self._anneal()
+        x = x.squeeze(0)
+        output = self.qf(x)
+        action = self.q_to_a(output)
+        if D.get_noise_mode() == "reference_cpu":
+            r = torch.Tensor(np.random.rand(*action.shape)).to(x.device)
+            random_action = torch.LongTensor(np.random.randint(low=0, high=self.action_shape, size=action.shape)).to(x.device)
+        else:
+            r = torch.rand(action.shape, device=x.device)
+            random_action = torch.randint(0, self.action_shape, action.shape, device=x.device)
+        action = torch.where(r < self.epsilon, random_action, action)
+        return {"q_value": output, "action": action}
+
+    def eval_act(self, x):
+        with torch.no_grad():
+            return self.q_to_a(self.qf(x))
+
+    def to(self, device):
+        self.qf.to(device)
+        return self
+
+    def parameters(self):
+        return self.qf.parameters()
+
+
+class EpsilonGreedyQRDQNDiscretePolicy(EpsilonGreedyDQNDiscretePolicy):
+    """Greedy w.r.t. the mean over quantiles (discrete_policies.py:77-89), batched."""
+
+    def __init__(self, quantile_num, **kwargs):
+        super().__init__(**kwargs)
+        self.quantile_num = quantile_num
+        self.continuous = False
+
+    def q_to_a(self, q):
+        q = q.view(q.shape[:-1] + (self.action_shape, self.quantile_num))
+        return q.mean(dim=-1).max(dim=-1, keepdim=True)[1].detach()
+
+
+class CategoricalDisPolicy(networks.Net):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self.continuous = False
+
+    def forward(self, x):
+        return torch.softmax(super().forward(x), dim=-1)
+
+    def explore(self, x, return_log_probs=False):
+        output = self.forward(x)
+        dis = Categorical(output)
+        action = dis.sample()
+        out = {"dis": output, "action": action}
+        if return_log_probs:
+            out["log_prob"] = dis.log_prob(action)
+        return out
+
+    def eval_act(self, x):
+        return self.forward(x).max(dim=-1)[1].detach()
+
+    def update(self, obs, actions):
+        dis = Categorical(self.forward(obs))
+        return {"dis": dis, "log_prob": dis.log_prob(actions).unsqueeze(-1), "ent": dis.entropy()}

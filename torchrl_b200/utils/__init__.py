@@ -1,0 +1,2 @@
+from .args import get_args, get_params  # noqa: F401
+from .logger import Logger, NullLogger  # noqa: F401
