@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the PPO hot path (rollout + GAE + update) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+A "step" is one PPO epoch of BASELINE.json configs[1]: 4096 synthetic HalfCheetah-shaped envs per
+GPU (obs 17, act 6), horizon 128, MLP(256,256) policy and value nets, 10 optimisation passes of
+32 minibatches (4 time-rows x all envs = 16384 samples per GPU): 524288 env-steps per GPU per step.
+With N > 1 every rank owns 4096 envs (weak scaling; configs[4] at N = 8) and the flat pf|vf
+gradient is all-reduced over NCCL once per minibatch.
+
+Prints ONE JSON line (rank 0).  `value` = device-timed (CUDA events, max over ranks) throughput
+with the host out of the loop (no per-epoch read-backs); `e2e` = the same metric through the
+public collector/agent API, wall-clock, including every host->device (minibatch row order,
+learning rates) and device->host (per-update logged scalars, episode returns) copy.
+`--impl reference` times the CPU restatement of the reference's path (oracle/ref_port.py --
+the reference itself is pure Python under /root/reference and cannot travel to the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_ENVS_PER_GPU = 4096
+HORIZON = 128
+HIDDEN = (256, 256)
+BATCH_ROWS = 4
+OPT_EPOCHS = 10
+OBS_DIM, ACT_DIM = 17, 6
+ENV_ID = "SynthHalfCheetah-v0"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=N_ENVS_PER_GPU)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0, help="env worker processes of the CPU arm (0 = auto)")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_pipeline_sample(env_nums, proc_nums, sample_steps, sample_minibatches, threads):
+    """Bounded sample of the CPU path (oracle/ref_port.py = the reference's algorithm, pinned to it by
+    tests/test_oracle_vs_reference.py): `sample_steps` collector steps over all `env_nums` envs through
+    the multi-process vec env, the Python GAE loop on a full-horizon buffer, and `sample_minibatches`
+    PPO minibatch updates of the full minibatch size.  The per-epoch time is composed from the three
+    measured rates:  T*N/collect_rate + gae + opt_epochs*(T/b)*t_minibatch."""
+    import numpy as np
+    import torch
+    from oracle import ref_port
+    torch.set_num_threads(threads)
+    env, col, agent = ref_port.build_ppo(env_id=ENV_ID, env_nums=env_nums, proc_nums=proc_nums, horizon=HORIZON,
+                                         hidden=HIDDEN, batch_rows=BATCH_ROWS, opt_epochs=OPT_EPOCHS, seed=0)
+    try:
+        col.train_rews = []
+        for _ in range(2):
+            col.step()                                            # warm-up (worker start-up, torch init)
+        t0 = time.perf_counter()
+        for _ in range(sample_steps):
+            col.step()
+        t_collect = (time.perf_counter() - t0) / sample_steps     # seconds per vec step
+        # fill the rest of the horizon with copies so GAE / minibatches see full-size float64 buffers
+        buf = agent.buffer
+        while buf.size < buf.rows:
+            buf.add({k: v[(buf.top - 1) % buf.rows] for k, v in buf.data.items() if k not in ("advs", "estimate_returns")})
+        t0 = time.perf_counter()
+        agent.process_epoch_samples()
+        t_gae = time.perf_counter() - t0
+        keys = ["obs", "acts", "advs", "estimate_returns", "values"]
+        it = buf.minibatches(BATCH_ROWS * env_nums, keys, True)
+        agent.update(next(it))                                    # warm-up
+        t0 = time.perf_counter()
+        n = 0
+        for batch in it:
+            agent.update(batch)
+            n += 1
+            if n >= sample_minibatches:
+                break
+        t_mb = (time.perf_counter() - t0) / max(n, 1)
+    finally:
+        env.close()
+    frames = HORIZON * env_nums
+    n_mb = OPT_EPOCHS * (HORIZON // BATCH_ROWS)
+    t_epoch = HORIZON * t_collect + t_gae + n_mb * t_mb
+    return {"env_steps_per_s": frames / t_epoch, "t_epoch_s": t_epoch, "collect_steps_per_s": env_nums / t_collect,
+            "gae_s": t_gae, "minibatch_s": t_mb, "sample_steps": sample_steps, "sample_minibatches": n}
+
+
+def auto_procs(env_nums, want=0):
+    cores = os.cpu_count() or 1
+    p = want or min(cores, 64)
+    while p > 1 and env_nums % p:
+        p -= 1
+    return max(p, 1), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    env_nums = args.envs_per_gpu
+    procs, cores = auto_procs(env_nums, args.cpu_procs)
+    threads = cores
+    vals, ms = [], []
+    for i in range(args.warmup + args.steps):
+        r = cpu_pipeline_sample(env_nums, procs, sample_steps=4, sample_minibatches=2, threads=threads)
+        if i >= args.warmup:
+            vals.append(r["env_steps_per_s"])
+            ms.append(r["t_epoch_s"] * 1e3)
+        last = r
+    value = sum(vals) / len(vals)
+    sample = ("per step: 4 collector steps x %d envs over %d spawned env workers + full-horizon Python GAE + 2 PPO "
+              "minibatches of %d samples on %d torch threads; epoch time composed as T*t_step + t_gae + %d*t_minibatch"
+              % (env_nums, procs, BATCH_ROWS * env_nums, threads, OPT_EPOCHS * (HORIZON // BATCH_ROWS)))
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 buffers / f32 nets",
+        "data": "synthetic",
+        "config": {"workload": "PPO SynthHalfCheetah-v0 (obs 17, act 6), %d envs, horizon %d, MLP%s, "
+                               "batch %d, %d opt epochs" % (env_nums, HORIZON, list(HIDDEN), BATCH_ROWS * env_nums,
+                                                            OPT_EPOCHS),
+                   "parallelism": "cpu: %d env worker processes, %d torch threads" % (procs, threads)},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "detail": {k: last[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s")}},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def build_agent(args, ctx, device):
+    import numpy as np
+    import torch
+    import torchrl_b200.networks as networks
+    import torchrl_b200.policies as policies
+    from torchrl_b200.algo import PPO
+    from torchrl_b200.collector import VecOnPolicyCollector
+    from torchrl_b200.env import get_vec_env
+    from torchrl_b200.replay_buffers import OnPolicyReplayBuffer
+    from torchrl_b200.utils import NullLogger
+    n_local = args.envs_per_gpu
+    n_total = n_local * ctx.world_size
+    first = ctx.rank * n_local
+    params = {"reward_scale": 1, "obs_norm": True}
+    env = get_vec_env(ENV_ID, params, n_local, device=device, first_env=first, total_envs=n_total)
+    eval_env = get_vec_env(ENV_ID, params, n_local, device=device, first_env=first, total_envs=n_total)
+    env.dist = ctx if ctx.active else None
+    env.seed(0)
+    torch.manual_seed(0)            # identical nets and identical minibatch row order on every rank
+    np.random.seed(0)
+    buf = OnPolicyReplayBuffer(env_nums=n_local, max_replay_buffer_size=HORIZON * n_local, time_limit_filter=True)
+    net = dict(hidden_shapes=list(HIDDEN), append_hidden_shapes=[], base_type=networks.MLPBase,
+               activation_func=torch.nn.Tanh)
+    pf = policies.GuassianContPolicyBasicBias(input_shape=OBS_DIM, output_shape=ACT_DIM, tanh_action=True, **net)
+    vf = networks.Net(input_shape=(OBS_DIM,), output_shape=1, **net)
+    col = VecOnPolicyCollector(vf, env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device=device,
+                               train_render=False, epoch_frames=HORIZON * n_local, max_episode_frames=999,
+                               eval_episodes=1, use_cuda_graph=not args.no_graph)
+    if ctx.active:
+        # decorrelate exploration noise across ranks (different envs, different Philox streams)
+        pf._rng_state(device).seed += 7919 * ctx.rank
+    agent = PPO(pf=pf, vf=vf, plr=3e-4, vlr=3e-4, clip_para=0.2, opt_epochs=OPT_EPOCHS, tau=0.95, shuffle=True,
+                entropy_coeff=0.005, env=env, replay_buffer=buf, collector=col, logger=NullLogger(), discount=0.99,
+                num_epochs=488, batch_size=BATCH_ROWS * n_local, gae=True, device=device, save_dir=None,
+                use_cuda_graph=not args.no_graph, dist=ctx if ctx.active else None)
+    return agent, col, buf, env
+
+
+def gae_roofline(device, iters=10):
+    """GAE scan on an L2-exceeding working set (T=128, N=2^20: 2.4 GB), L2 flushed between launches."""
+    import torch
+    from torchrl_b200 import ops
+    T, N = 128, 1 << 20
+    R = torch.randn(T, N, device=device)
+    V = torch.randn(T, N, device=device)
+    Tm = (torch.rand(T, N, device=device) < 0.01).to(torch.uint8)
+    TL = (torch.rand(T, N, device=device) < 0.005).to(torch.uint8)
+    LV = torch.randn(N, device=device)
+    A, Rt = torch.empty_like(R), torch.empty_like(R)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    for _ in range(3):
+        ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, A, Rt)
+    times = []
+    for _ in range(iters):
+        flush.fill_(1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, A, Rt)
+        e.record()
+        torch.cuda.synchronize(device)
+        times.append(s.elapsed_time(e) * 1e-3)
+    avg = sum(times) / len(times)
+    alg_bytes = 18 * T * N + 4 * N
+    del R, V, Tm, TL, LV, A, Rt, flush
+    torch.cuda.empty_cache()
+    return alg_bytes, avg
+
+
+def gae_in_step_time(agent, buf, iters=20):
+    """Duration of the GAE launch at the config's own size (T=128, N=4096: 9.4 MB, L2-resident)."""
+    import torch
+    with torch.no_grad():
+        lv = torch.zeros(buf.env_nums, device=agent.device)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    buf.generalized_advantage_estimation(lv, 0.99, 0.95)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        buf.generalized_advantage_estimation(lv, 0.99, 0.95)
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) * 1e-3 / iters
+
+
+def run_ours(args):
+    import torch
+    from torchrl_b200 import _lib
+    from torchrl_b200.distributed import DataParallelContext
+    ctx = DataParallelContext()
+    if ctx.world_size != args.gpus and ctx.world_size > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, ctx.world_size))
+    device = ctx.device
+    if device.type != "cuda":
+        raise SystemExit("bench.py needs a CUDA device (no CPU path in the product)")
+    _lib.load()                                           # fail loudly if the native library is missing
+    agent, col, buf, env = build_agent(args, ctx, device)
+    frames_per_step = HORIZON * args.envs_per_gpu * ctx.world_size
+
+    def epoch(host_io):
+        agent.current_epoch = 0
+        if host_io:
+            col.train_one_epoch()
+            agent.update_per_epoch()
+        else:
+            col.rollout_no_sync()
+            agent.update_per_epoch(flush_infos=False)
+
+    for _ in range(max(args.warmup, 3)):
+        epoch(True)
+    for _ in range(2):
+        epoch(False)
+    torch.cuda.synchronize(device)
+
+    # ---- value: device-timed, host out of the loop ------------------------------------------
+    sampler = ClockSampler(ctx.local_rank)
+    launches0 = _lib.launch_count()
+    ctx.barrier()
+    torch.cuda.synchronize(device)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        epoch(False)
+    ev1.record()
+    torch.cuda.synchronize(device)
+    ctx.barrier()
+    clocks = sampler.stop()
+    t_dev = ctx.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    launches = _lib.launch_count() - launches0
+
+    # ---- e2e: public API, wall clock, host copies inside ---------------------------------------
+    ctx.barrier()
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        epoch(True)
+    torch.cuda.synchronize(device)
+    ctx.barrier()
+    t_e2e = ctx.max_over_ranks(time.perf_counter() - t0)
+
+    value = frames_per_step * args.steps / t_dev
+    e2e_value = frames_per_step * args.steps / t_e2e
+    st = agent._mb_state
+    h2d = st["perm_host"].numel() * 8 + agent.opt.lr_host.numel() * 4 * 2
+    d2h = st["log32"].numel() * 4 + st["log64"].numel() * 8 + 4 + 4 + 8 * args.envs_per_gpu
+
+    roofline = None
+    if ctx.rank == 0 and not args.skip_roofline:
+        peak, how = measured_peaks()
+        alg_bytes, dur = gae_roofline(device)
+        t_small = gae_in_step_time(agent, buf)
+        traffic = None
+        pj = os.path.join(ROOT, "profiles", "gae_scan_ncu_summary.json")
+        if os.path.exists(pj):
+            traffic = json.load(open(pj)).get("dram_bytes_per_launch")
+        roofline = {"kernel": "gae_chunked_kernel<GAE,VEC=4,TC=4>", "bound": "hbm",
+                    "workload": "T=128 x N=2^20 rollout (2.42 GB algorithmic), L2 flushed between launches",
+                    "achieved": alg_bytes / dur / 1e9, "peak": peak, "peak_source": how, "unit": "GB/s",
+                    "frac": alg_bytes / dur / 1e9 / peak, "traffic": traffic,
+                    "algorithmic_bytes_per_launch": alg_bytes, "launch_us": dur * 1e6,
+                    "in_step": {"workload": "T=128 x N=%d (9.4 MB, L2-resident): latency-bound" % args.envs_per_gpu,
+                                "launch_us": t_small * 1e6,
+                                "achieved_GBs": (18 * HORIZON * args.envs_per_gpu) / t_small / 1e9}}
+
+    cpu_baseline = None
+    if ctx.rank == 0 and args.gpus == 1 and not args.skip_cpu_baseline:
+        procs, cores = auto_procs(args.envs_per_gpu, args.cpu_procs)
+        r = cpu_pipeline_sample(args.envs_per_gpu, procs, sample_steps=6, sample_minibatches=3, threads=cores)
+        cpu_baseline = {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": cores, "kind": "port",
+                        "sample": "6 collector steps x %d envs over %d spawned env workers + full-horizon Python GAE "
+                                  "+ 3 PPO minibatches of %d samples (%d torch threads); epoch time composed from the "
+                                  "three rates" % (args.envs_per_gpu, procs, BATCH_ROWS * args.envs_per_gpu, cores),
+                        "detail": {k: r[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s", "t_epoch_s")}}
+
+    if ctx.rank == 0:
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": ctx.world_size,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "PPO SynthHalfCheetah-v0 (obs 17, act 6), %d envs/GPU x %d GPU, horizon %d, "
+                                   "MLP%s, minibatch %d/GPU, %d opt epochs (BASELINE.json configs[%d])"
+                                   % (args.envs_per_gpu, ctx.world_size, HORIZON, list(HIDDEN),
+                                      BATCH_ROWS * args.envs_per_gpu, OPT_EPOCHS, 1 if ctx.world_size == 1 else 4),
+                       "global_envs": args.envs_per_gpu * ctx.world_size,
+                       "parallelism": "dp%d (env sharding, NCCL all-reduce of the flat gradient)" % ctx.world_size,
+                       "matmul": "fp32 cuBLAS (TF32 off)", "cuda_graphs": not args.no_graph,
+                       "l2": "each step rewrites the whole 100 MB rollout working set and all activations "
+                             "(> 126 MB L2 per epoch); the GAE roofline launch flushes L2 explicitly"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if roofline is not None:
+            line["roofline"] = roofline
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    ctx.destroy()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -28,12 +28,15 @@ time limit (like HalfCheetah).  ``SynthAnt-v0``: o=111, a=8, terminates when
 """
 import numpy as np
 
-try:  # the shim (oracle/shims) or a real gym, whichever is on sys.path
+try:  # a real gym if one is installed ...
     import gym
     from gym import spaces
-except ImportError:  # pragma: no cover
-    gym = None
-    spaces = None
+except ImportError:  # ... else the stand-in under oracle/shims (real package on sys.path: spawned workers re-import)
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims"))
+    import gym
+    from gym import spaces
 
 RHO = 0.8
 ETA = 0.5
@@ -97,7 +100,7 @@ def dynamics(s, u, A, B, c, term_thr):
     return s2, r, done
 
 
-class SynthMJCore(gym.Env if gym is not None else object):
+class SynthMJCore(gym.Env):
     """One synthetic MuJoCo-shaped env with the (old) gym API."""
 
     def __init__(self, env_id):
@@ -129,7 +132,7 @@ class SynthMJCore(gym.Env if gym is not None else object):
         return self.state.copy(), float(r[0]), bool(done[0]), {}
 
 
-class TimeLimit(gym.Wrapper if gym is not None else object):
+class TimeLimit(gym.Wrapper):
     """gym-0.10-style time limit.  The class *name* matters: the reference adds its
     TimeLimitAugment wrapper only if the made env's class name contains 'TimeLimit'
     (/root/reference/torchrl/env/get_env.py:54)."""
@@ -155,6 +158,6 @@ def make_env(env_id, max_episode_steps=MAX_EPISODE_STEPS):
     return TimeLimit(SynthMJCore(env_id), max_episode_steps)
 
 
-if gym is not None and hasattr(gym, "register") and hasattr(gym, "_REGISTRY"):
+if hasattr(gym, "register") and hasattr(gym, "_REGISTRY"):
     for _eid in SPECS:
         gym.register(_eid, (lambda eid: (lambda **kw: make_env(eid, **kw)))(_eid))

@@ -1,0 +1,125 @@
+"""Pins the oracle against the UNMODIFIED reference (only where /root/reference exists).
+
+The reference has no tests or golden vectors, so the pin is: run the
+reference's own collector + buffer + PPO and the oracle port (oracle/ref_port.py) from the same
+seeds and require identical rollouts, advantages, parameters and logged scalars.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.reference
+
+
+class _NullLogger:
+    def __init__(self):
+        self.infos = []
+
+    def add_update_info(self, info):
+        self.infos.append(info)
+
+    def add_epoch_info(self, *a, **k):
+        pass
+
+    def log(self, *a):
+        pass
+
+    def finish(self):
+        pass
+
+
+def _reference_ppo(N, T, hidden, batch_rows, opt_epochs, seed, max_frames, tmp_path):
+    import torch
+    from oracle import reference_loader
+    reference_loader.load()
+    import torchrl.networks as networks
+    import torchrl.policies as policies
+    from torchrl.algo import PPO
+    from torchrl.collector.on_policy import VecOnPolicyCollector
+    from torchrl.env import get_vec_env
+    from torchrl.replay_buffers.on_policy import OnPolicyReplayBuffer
+    params = {"reward_scale": 1, "obs_norm": True}
+    env = get_vec_env("SynthHalfCheetah-v0", dict(params), N)
+    eval_env = get_vec_env("SynthHalfCheetah-v0", dict(params), N)
+    env.seed(seed)
+    torch.manual_seed(seed)
+    np.random.seed(seed)
+    buf = OnPolicyReplayBuffer(env_nums=N, max_replay_buffer_size=T * N, time_limit_filter=True)
+    net = dict(hidden_shapes=list(hidden), append_hidden_shapes=[], base_type=networks.MLPBase,
+               activation_func=torch.nn.Tanh)
+    pf = policies.GuassianContPolicyBasicBias(input_shape=env.observation_space.shape[0],
+                                              output_shape=env.action_space.shape[0], tanh_action=True, **net)
+    vf = networks.Net(input_shape=env.observation_space.shape, output_shape=1, **net)
+    col = VecOnPolicyCollector(vf, env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device="cpu",
+                               train_render=False, epoch_frames=T * N, max_episode_frames=max_frames, eval_episodes=1)
+    logger = _NullLogger()
+    agent = PPO(pf=pf, vf=vf, plr=3e-4, vlr=3e-4, clip_para=0.2, opt_epochs=opt_epochs, tau=0.95, shuffle=True,
+                entropy_coeff=0.005, env=env, replay_buffer=buf, collector=col, logger=logger, discount=0.99,
+                num_epochs=488, batch_size=batch_rows * N, gae=True, device="cpu", save_dir=str(tmp_path))
+    return env, col, agent, buf, logger
+
+
+@pytest.mark.parametrize("max_frames", [999, 7])
+def test_port_reproduces_reference_ppo(tmp_path, max_frames):
+    """Both pipelines consume the GLOBAL torch / NumPy generators, so each is run to completion
+    from its own seeding before the other starts."""
+    from oracle import ref_port
+    N, T, hidden, rows, oe, seed = 4, 16, (16, 16), 4, 2, 3
+    keys = ("obs", "next_obs", "acts", "values", "rewards", "terminals", "time_limits")
+
+    renv, rcol, ragent, rbuf, rlog = _reference_ppo(N, T, hidden, rows, oe, seed, max_frames, tmp_path)
+    r_rec = []
+    for epoch in range(2):
+        ragent.current_epoch = epoch
+        out = rcol.train_one_epoch()
+        roll = {k: getattr(rbuf, "_" + k).copy() for k in keys}
+        ragent.update_per_epoch()
+        r_rec.append((out["train_epoch_reward"], roll, rbuf._advs.copy(), rbuf._estimate_returns.copy()))
+    r_params = [p.detach().numpy().copy() for p in list(ragent.pf.parameters()) + list(ragent.vf.parameters())]
+
+    penv, pcol, pagent = ref_port.build_ppo(env_nums=N, horizon=T, hidden=hidden, batch_rows=rows, opt_epochs=oe,
+                                            seed=seed, max_episode_frames=max_frames)
+    for epoch in range(2):
+        pagent.current_epoch = epoch
+        out = pcol.train_one_epoch()
+        rew, roll, advs, rets = r_rec[epoch]
+        assert out["train_epoch_reward"] == rew
+        for k in keys:
+            np.testing.assert_array_equal(roll[k], pagent.buffer.data[k], err_msg=k)
+        pagent.update_per_epoch()
+        np.testing.assert_array_equal(advs, pagent.buffer.data["advs"])
+        np.testing.assert_array_equal(rets, pagent.buffer.data["estimate_returns"])
+    p_params = [p.detach().numpy() for p in list(pagent.pf.parameters()) + list(pagent.vf.parameters())]
+    # the port keeps `logstd` after the net parameters; the reference registers it first
+    key = lambda a: (a.shape, float(np.abs(a).sum()))
+    assert sorted(map(key, r_params)) == sorted(map(key, p_params))
+    assert len(rlog.infos) == len(pagent.infos) == 2 * oe * (T // rows)
+    for a, b in zip(rlog.infos, pagent.infos):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k] == b[k], k
+    nrm = renv._obs_normalizer
+    np.testing.assert_array_equal(nrm._mean, penv.norm.mean)
+    np.testing.assert_array_equal(nrm._var, penv.norm.var)
+    assert nrm._count == penv.norm.count
+
+
+def test_numpy_oracle_pieces_against_reference_functions():
+    """Normalizer, NormAct, quantile loss, soft update: ref_numpy vs the reference's own functions."""
+    import torch
+    from oracle import reference_loader, ref_numpy as rn
+    reference_loader.load()
+    from torchrl.env.base_wrapper import Normalizer
+    import torchrl.algo.utils as atu
+    rs = np.random.RandomState(0)
+    ref, mine = Normalizer((5,)), rn.RunningNorm(5)
+    for _ in range(4):
+        x = rs.randn(9, 5) * 3 + 1
+        ref.update_estimate(x)
+        mine.update(x)
+        np.testing.assert_array_equal(ref.filt(x), mine.filt(x))
+    np.testing.assert_array_equal(ref._mean, mine.mean)
+    np.testing.assert_array_equal(ref._var, mine.var)
+    tau = (2 * np.arange(7) + 1) / 14.0
+    src, tgt = rs.randn(6, 7), rs.randn(6, 7)
+    ref_l = atu.quantile_regression_loss(torch.tensor(tau).view(1, -1), torch.tensor(src), torch.tensor(tgt)).item()
+    assert abs(ref_l - rn.quantile_regression_loss(tau, src, tgt)) < 1e-12

@@ -57,14 +57,18 @@ def test_graph_and_eager_paths_agree():
     (a0, b0, i0), (a1, b1, i1) = runs
     for k in ("obs", "next_obs", "acts", "values", "rewards", "terminals", "time_limits", "advs",
               "estimate_returns", "old_logp"):
-        torch.testing.assert_close(getattr(b0, "_" + k), getattr(b1, "_" + k), rtol=0, atol=0)
-    torch.testing.assert_close(a0.opt.data, a1.opt.data, rtol=0, atol=0)
+        x0, x1 = getattr(b0, "_" + k), getattr(b1, "_" + k)
+        if x0.dtype == torch.uint8:
+            assert torch.equal(x0, x1), k
+        else:   # cuBLAS may pick different algorithms under capture: allow fp32 round-off, not more
+            torch.testing.assert_close(x0, x1, rtol=1e-4, atol=1e-5, msg=k)
+    torch.testing.assert_close(a0.opt.data, a1.opt.data, rtol=1e-4, atol=1e-6)
     for (r0, u0), (r1, u1) in zip(i0, i1):
-        assert r0 == r1 and len(u0) == len(u1) == 2 * 4
+        assert abs(r0 - r1) <= 1e-4 * max(1.0, abs(r0)) and len(u0) == len(u1) == 2 * 4
         for d0, d1 in zip(u0, u1):
             assert d0.keys() == d1.keys()
             for k in d0:
-                assert d0[k] == d1[k] or (np.isnan(d0[k]) and np.isnan(d1[k])), k
+                assert abs(d0[k] - d1[k]) <= 1e-3 * max(1.0, abs(d0[k])) or (np.isnan(d0[k]) and np.isnan(d1[k])), k
 
 
 @pytest.mark.gpu

@@ -92,8 +92,24 @@ def check(rc, name):
         raise RuntimeError("%s failed (rc=%d): %s" % (name, rc, msg.decode() if msg else ""))
 
 
+_LAUNCHES = 0
+
+
+def launch_count():
+    """Kernels launched through the C ABI so far (graph replays add their captured count)."""
+    return _LAUNCHES
+
+
+def add_launches(n):
+    global _LAUNCHES
+    _LAUNCHES += int(n)
+
+
 def call(name, *args):
+    """Invoke a kernel-launching entry point (each launches exactly one kernel) and raise on error."""
+    global _LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         check(rc, name)
+    _LAUNCHES += 1

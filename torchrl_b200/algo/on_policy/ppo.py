@@ -107,7 +107,10 @@ class PPO(A2C):
         info = st["info"][0]
         adv_stats = info[20:24]
         advs = batch["advs"].reshape(-1)
-        ops.vec_stats(advs, out=adv_stats)
+        if self.dist is not None and self.dist.active:
+            self.dist.global_vec_stats(advs, adv_stats)      # moments span all ranks' envs (ppo.py:147)
+        else:
+            ops.vec_stats(advs, out=adv_stats)
         # critic
         v = self.vf(batch["obs"])
         g_v, _ = ops.ppo_critic_loss(v.reshape(-1), batch["estimate_returns"].reshape(-1),
@@ -138,9 +141,7 @@ class PPO(A2C):
             self._mb_eager_runs += 1
             self._mb_body()
         else:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._mb_body()
+            g = ops.CapturedGraph(self._mb_body)
             self._mb_graph = g
             g.replay()
         self.training_update_num += 1
@@ -165,8 +166,10 @@ class PPO(A2C):
         return infos
 
     # ------------------------------------------------------------------ reference API
-    def update_per_epoch(self):
-        """ppo.py:27-39: GAE, linear LR decay, target <- pf, opt_epochs passes of minibatches."""
+    def update_per_epoch(self, flush_infos=True):
+        """ppo.py:27-39: GAE, linear LR decay, target <- pf, opt_epochs passes of minibatches.
+        flush_infos=False skips the end-of-epoch read-back of the logged scalars (benchmarking the
+        device path alone)."""
         self.process_epoch_samples()
         atu.update_linear_schedule(self.pf_optimizer, self.current_epoch, self.num_epochs, self.plr)
         atu.update_linear_schedule(self.vf_optimizer, self.current_epoch, self.num_epochs, self.vlr)
@@ -184,6 +187,8 @@ class PPO(A2C):
         n = st["U"]
         for _ in range(n):
             self._run_minibatch()
+        if not flush_infos:
+            return
         self._last_infos = self._flush_infos(n)
         if self.logger is not None:
             for info in self._last_infos:

@@ -172,9 +172,7 @@ class VecCollector:
             self._eager_steps += 1          # warm-up: real steps, executed eagerly
             self._step_body(boot)
         else:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._step_body(boot)
+            g = ops.CapturedGraph(lambda: self._step_body(boot))
             self._graphs[boot] = g
             g.replay()                      # capture does not execute: run the step now
         self._host_after_step()
@@ -194,12 +192,8 @@ class VecCollector:
 
     def train_one_epoch(self):
         """T = epoch_frames // env_nums steps (collector/base.py:108-122, :179).  One host sync at the end."""
-        self.env.train()
-        self._epoch_reward.zero_()
-        self._n_done.zero_()
         top0 = self.replay_buffer._top
-        for _ in range(self.sample_epoch_frames):
-            self._step()
+        self.rollout_no_sync()
         n_done = int(self._n_done.item())                   # the epoch's only sync
         if int(self._nan_flag.item()) != 0:
             raise FloatingPointError("NaN detected in sampled actions (reference: 'NaN detected. BOOM')")
@@ -210,9 +204,18 @@ class VecCollector:
             log = self._ret_log[rows]
             m = ~torch.isnan(log)
             self.train_rews = [float(x) for x in log[m].cpu().numpy()]
-            self._ret_log[rows] = float("nan")
         self.train_epoch_reward = float(self._epoch_reward.sum().item())
         return {'train_rewards': self.train_rews, 'train_epoch_reward': self.train_epoch_reward}
+
+    def rollout_no_sync(self):
+        """The T collector steps of one epoch with no host read-back at all (what train_one_epoch
+        runs before fetching its summary)."""
+        self.env.train()
+        self._epoch_reward.zero_()
+        self._n_done.zero_()
+        self._ret_log.fill_(float("nan"))
+        for _ in range(self.sample_epoch_frames):
+            self._step()
 
     def eval_one_epoch(self):
         """Deterministic-policy evaluation episodes on the eval env (collector/base.py:232-280)."""

@@ -133,8 +133,9 @@ class SynthVecEnv:
         self._obs = None
         self._host_elapsed = 0          # host mirror of `elapsed` (valid while lockstep and unperturbed)
         self._host_mirror_ok = True
-        # stats merge happens in-kernel unless a distributed collector asks for the raw batch sums
-        self.merge_in_kernel = True
+        # stats merge happens in-kernel; with a DataParallelContext the batch sums are all-reduced
+        # over ranks first and merged by a separate launch (global statistics)
+        self.dist = None
         self.seed(0)
 
     # ------------------------------------------------------------------ reference API
@@ -165,7 +166,13 @@ class SynthVecEnv:
             self.obs_out.copy_(self.state)
             return self.obs_out
         if update and self.training:
-            self._obs_normalizer.update_estimate(self.state)
+            if self.dist is not None and self.dist.active:
+                sums = ops.obs_norm_moments(self.state, self.batch_sums)
+                self.dist.all_reduce_sum_(sums)
+                nrm = self._obs_normalizer
+                ops.obs_norm_merge(sums, self.total_envs, nrm._mean, nrm._var, nrm._count)
+            else:
+                self._obs_normalizer.update_estimate(self.state)
         return self._obs_normalizer.filt(self.state, out=self.obs_out)
 
     def reset(self, **kwargs):
@@ -189,6 +196,7 @@ class SynthVecEnv:
         N, o, a = self.env_nums, self.obs_dim, self.act_dim
         update = self.obs_norm and self.training and self._obs_normalizer.should_estimate
         nrm = self._obs_normalizer
+        distributed = self.dist is not None and self.dist.active
         rs = float(self._reward_scale) if self.training else 1.0
         _lib.call("trl_synth_env_step", self.state.data_ptr(), ops._chk(actions, F32, "actions"),
                   self.A.data_ptr(), self.B.data_ptr(), self.c.data_ptr(), self.lb.data_ptr(), self.ub.data_ptr(),
@@ -201,7 +209,10 @@ class SynthVecEnv:
                   N, o, a, spec.RHO, spec.ETA, spec.CTRL_COST,
                   float(self.term_thr) if np.isfinite(self.term_thr) else 3.0e38, rs, self._max_episode_steps,
                   int(max_episode_frames) if step_count is not None else (1 << 30),
-                  1 if (update and self.merge_in_kernel) else 0, ops._stream())
+                  1 if (update and not distributed) else 0, ops._stream())
+        if update and distributed:
+            self.dist.all_reduce_sum_(self.batch_sums)
+            ops.obs_norm_merge(self.batch_sums, self.total_envs, nrm._mean, nrm._var, nrm._count)
         if self.obs_norm:
             ops.obs_norm_filt(self.state, nrm._mean, nrm._var, nrm.clip, self.obs_out)
         return self.obs_out

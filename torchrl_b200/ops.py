@@ -18,6 +18,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+class CapturedGraph:
+    """torch.cuda.CUDAGraph capture of `fn` that also remembers how many library kernels it holds,
+    so that replays keep `_lib.launch_count()` truthful."""
+
+    def __init__(self, fn):
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            fn()
+        self.launches = _lib.launch_count() - before
+        _lib.add_launches(-self.launches)          # capture records, it does not execute
+
+    def replay(self):
+        self.graph.replay()
+        _lib.add_launches(self.launches)
+
+
 def _chk(t, dtype, name):
     if not t.is_cuda:
         raise ValueError("%s must be a CUDA tensor (torchrl_b200 has no CPU path)" % name)

@@ -198,6 +198,10 @@ class GuassianContPolicyBasicBias(networks.Net, GuassianContPolicyBase):
     def mean_net(self, x):
         return networks.Net.forward(self, x)
 
+    def mean_params(self):
+        """Parameters of the mean network only (everything but the free log-std)."""
+        return [p for n, p in self.named_parameters() if n != "logstd"]
+
     def clamped_logstd(self):
         return torch.clamp(self.logstd, LOG_SIG_MIN, LOG_SIG_MAX)
 
