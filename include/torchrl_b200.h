@@ -134,6 +134,34 @@ int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
                   float grad_scale, int zero_grad, void* stream);
 int trl_polyak_update(float* target, const float* source, int64_t n, float tau, void* stream);
 
+/* ---- K10: off-policy TD targets and loss reductions.
+ * TwinSACQ.update (algo/off_policy/twin_sac_q.py:84-219), TD3.update (algo/off_policy/td3.py:57-154),
+ * QRDQN.update (algo/off_policy/qrdqn.py:22-74) + quantile_regression_loss/huber (algo/utils.py:5-13),
+ * DQN.update (algo/off_policy/dqn.py:38-74). */
+int64_t trl_offpolicy_scratch_doubles(int64_t B);
+/* y = r + (1-d)*gamma*(min(q1',q2') - alpha*logpi')   (logp_next NULL -> TD3 form; q2_next NULL -> one critic) */
+int trl_td_target(const float* rewards, const uint8_t* terminals, const float* q1_next, const float* q2_next,
+                  const float* logp_next, const float* log_alpha, float fixed_alpha, float gamma, int64_t B,
+                  float* y, float* info1, double* scratch, unsigned* ticket, void* stream);
+/* a' = clamp(a + clamp(sigma*eps, +-c), +-1); eps NULL -> Philox noise   (td3.py:75-84) */
+int trl_td3_smooth_action(const float* action, const float* eps, float sigma, float noise_clip, uint64_t seed,
+                          const uint64_t* rng_counter, int64_t n, float* out, void* stream);
+/* alpha loss + its one-parameter Adam step (twin_sac_q.py:111-123); info2 = [alpha, alpha_loss] */
+int trl_sac_alpha_step(const float* logp, float target_entropy, float* log_alpha, float* adam_state3, float lr,
+                       float beta1, float beta2, float eps, int64_t B, float* info2, double* scratch,
+                       unsigned* ticket, void* stream);
+/* mean(alpha*logpi - min(q1,q2)) and its gradients (twin_sac_q.py:145-153); info5 = [loss, logp mean/std/max/min] */
+int trl_sac_policy_loss(const float* logp, const float* q1, const float* q2, const float* log_alpha,
+                        float fixed_alpha, int64_t B, float* g_logp, float* g_q1, float* g_q2, float* info5,
+                        double* scratch, unsigned* ticket, void* stream);
+/* MSE of one or two critics against the same target (twin_sac_q.py:142-143, td3.py:96-97) */
+int trl_twin_mse_loss(const float* q1, const float* q2, const float* y, int64_t B, float* g1, float* g2,
+                      float* info2, double* scratch, unsigned* ticket, void* stream);
+/* fused QR-DQN / DQN loss incl. greedy target selection; info3 = [loss, mean q_s_a, mean reward] */
+int trl_qr_dqn_loss(const float* pred, const float* next, const float* actions, const float* rewards,
+                    const uint8_t* terminals, int B, int n_actions, int n_quantiles, float gamma, float kappa,
+                    int mse, float* grad, float* info3, double* scratch, unsigned* ticket, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

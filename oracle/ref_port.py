@@ -405,3 +405,124 @@ def build_ppo(env_id="SynthHalfCheetah-v0", env_nums=8, proc_nums=0, horizon=128
     col = OnPolicyVecCollector(env, pf, vf, buf, horizon * env_nums, max_episode_frames, 0.99)
     agent = PPOPort(pf, vf, buf, opt_epochs=opt_epochs, batch_size=batch_rows * env_nums, num_epochs=num_epochs)
     return env, col, agent
+
+
+# ======================================================================================= off-policy
+def _polyak(net, target, tau):
+    for tp, p in zip(target.parameters(), net.parameters()):
+        tp.data.copy_(tp.data * (1.0 - tau) + p.data * tau)
+
+
+class SACPort:
+    """TwinSACQ.update (algo/off_policy/twin_sac_q.py:84-219): automatic temperature, twin critics,
+    reparameterised policy loss, three Adam steps, Polyak targets."""
+
+    def __init__(self, pf, qf1, qf2, act_dim, plr=3e-4, qlr=3e-4, discount=0.99, tau=0.005, std_reg=0.0,
+                 mean_reg=0.0, grad_clip=None):
+        self.pf, self.qf1, self.qf2 = pf, qf1, qf2
+        self.tqf1, self.tqf2 = copy.deepcopy(qf1), copy.deepcopy(qf2)
+        self.q1_opt = torch.optim.Adam(qf1.parameters(), lr=qlr)
+        self.q2_opt = torch.optim.Adam(qf2.parameters(), lr=qlr)
+        self.pf_opt = torch.optim.Adam(pf.parameters(), lr=plr)
+        self.target_entropy = -float(act_dim)
+        self.log_alpha = torch.zeros(1, requires_grad=True)
+        self.alpha_opt = torch.optim.Adam([self.log_alpha], lr=plr)
+        self.discount, self.tau, self.std_reg, self.mean_reg, self.grad_clip = discount, tau, std_reg, mean_reg, grad_clip
+
+    def update(self, batch):
+        rewards = torch.Tensor(batch["rewards"])
+        terminals = torch.Tensor(batch["terminals"])
+        obs = torch.Tensor(batch["obs"])
+        actions = torch.Tensor(batch["acts"])
+        next_obs = torch.Tensor(batch["next_obs"])
+        s = self.pf.explore(obs, return_log_probs=True)
+        mean, log_std, new_actions, log_probs = s["mean"], s["log_std"], s["action"], s["log_prob"]
+        q1_pred = self.qf1([obs, actions])
+        q2_pred = self.qf2([obs, actions])
+        alpha_loss = -(self.log_alpha * (log_probs + self.target_entropy).detach()).mean()
+        self.alpha_opt.zero_grad()
+        alpha_loss.backward()
+        self.alpha_opt.step()
+        alpha = self.log_alpha.exp().detach()
+        with torch.no_grad():
+            t = self.pf.explore(next_obs, return_log_probs=True)
+            tq = torch.min(self.tqf1([next_obs, t["action"]]), self.tqf2([next_obs, t["action"]]))
+            target_v = tq - alpha * t["log_prob"]
+        q_target = rewards + (1.0 - terminals) * self.discount * target_v
+        qf1_loss = nn.functional.mse_loss(q1_pred, q_target.detach())
+        qf2_loss = nn.functional.mse_loss(q2_pred, q_target.detach())
+        q_new = torch.min(self.qf1([obs, new_actions]), self.qf2([obs, new_actions]))
+        policy_loss = (alpha * log_probs - q_new).mean()
+        policy_loss = policy_loss + self.std_reg * (log_std ** 2).mean() + self.mean_reg * (mean ** 2).mean()
+        for opt, loss, net in ((self.pf_opt, policy_loss, self.pf), (self.q1_opt, qf1_loss, self.qf1),
+                               (self.q2_opt, qf2_loss, self.qf2)):
+            opt.zero_grad()
+            loss.backward()
+            if self.grad_clip:
+                torch.nn.utils.clip_grad_norm_(net.parameters(), self.grad_clip)
+            opt.step()
+        _polyak(self.qf1, self.tqf1, self.tau)
+        _polyak(self.qf2, self.tqf2, self.tau)
+        info = {"Reward_Mean": rewards.mean().item(), "Alpha": alpha.item(), "Alpha_loss": alpha_loss.item(),
+                "Training/policy_loss": policy_loss.item(), "Training/qf1_loss": qf1_loss.item(),
+                "Training/qf2_loss": qf2_loss.item()}
+        for name, t_ in (("log_std", log_std), ("log_probs", log_probs), ("mean", mean)):
+            info[name + "/mean"] = t_.mean().item()
+            info[name + "/std"] = t_.std().item()
+            info[name + "/max"] = t_.max().item()
+            info[name + "/min"] = t_.min().item()
+        return info
+
+
+class TD3Port:
+    """TD3.update (algo/off_policy/td3.py:57-154), including the inverted delay test (:124)."""
+
+    def __init__(self, pf, qf1, qf2, plr=3e-4, qlr=3e-4, discount=0.99, tau=0.005, policy_update_delay=2,
+                 norm_std_policy=0.2, noise_clip=0.5):
+        self.pf, self.qf1, self.qf2 = pf, qf1, qf2
+        self.tpf, self.tqf1, self.tqf2 = copy.deepcopy(pf), copy.deepcopy(qf1), copy.deepcopy(qf2)
+        self.pf_opt = torch.optim.Adam(pf.parameters(), lr=plr)
+        self.q1_opt = torch.optim.Adam(qf1.parameters(), lr=qlr)
+        self.q2_opt = torch.optim.Adam(qf2.parameters(), lr=qlr)
+        self.discount, self.tau, self.delay = discount, tau, policy_update_delay
+        self.norm_std_policy, self.noise_clip = norm_std_policy, noise_clip
+        self.n = 0
+
+    def update(self, batch):
+        self.n += 1
+        obs = torch.Tensor(batch["obs"])
+        actions = torch.Tensor(batch["acts"])
+        next_obs = torch.Tensor(batch["next_obs"])
+        rewards = torch.Tensor(batch["rewards"])
+        terminals = torch.Tensor(batch["terminals"])
+        target_actions = self.tpf.explore(next_obs)["action"]
+        noise = torch.distributions.Normal(torch.zeros(target_actions.size()),
+                                           self.norm_std_policy * torch.ones(target_actions.size())).sample()
+        target_actions = target_actions + torch.clamp(noise, -self.noise_clip, self.noise_clip)
+        target_actions = torch.clamp(target_actions, -1, 1)
+        target_q = torch.min(self.tqf1([next_obs, target_actions]), self.tqf2([next_obs, target_actions]))
+        q_target = rewards + (1.0 - terminals) * self.discount * target_q
+        q1_pred, q2_pred = self.qf1([obs, actions]), self.qf2([obs, actions])
+        qf1_loss = nn.functional.mse_loss(q1_pred, q_target.detach())
+        qf2_loss = nn.functional.mse_loss(q2_pred, q_target.detach())
+        for opt, loss in ((self.q1_opt, qf1_loss), (self.q2_opt, qf2_loss)):
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        info = {"Reward_Mean": rewards.mean().item(), "Training/qf1_loss": qf1_loss.item(),
+                "Training/qf2_loss": qf2_loss.item()}
+        if self.n % self.delay:
+            new_actions = self.pf(obs)
+            policy_loss = -self.qf1([obs, new_actions]).mean()
+            self.pf_opt.zero_grad()
+            policy_loss.backward()
+            self.pf_opt.step()
+            _polyak(self.pf, self.tpf, self.tau)
+            _polyak(self.qf1, self.tqf1, self.tau)
+            _polyak(self.qf2, self.tqf2, self.tau)
+            info["Training/policy_loss"] = policy_loss.item()
+            info["new_actions/mean"] = new_actions.mean().item()
+            info["new_actions/std"] = new_actions.std().item()
+            info["new_actions/max"] = new_actions.max().item()
+            info["new_actions/min"] = new_actions.min().item()
+        return info

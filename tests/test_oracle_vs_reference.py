@@ -123,3 +123,85 @@ def test_numpy_oracle_pieces_against_reference_functions():
     src, tgt = rs.randn(6, 7), rs.randn(6, 7)
     ref_l = atu.quantile_regression_loss(torch.tensor(tau).view(1, -1), torch.tensor(src), torch.tensor(tgt)).item()
     assert abs(ref_l - rn.quantile_regression_loss(tau, src, tgt)) < 1e-12
+
+
+def _ref_offpolicy_nets(kind, o, a, hidden, seed):
+    import torch
+    from oracle import reference_loader
+    reference_loader.load()
+    import torchrl.networks as networks
+    import torchrl.policies as policies
+    torch.manual_seed(seed)
+    net = dict(hidden_shapes=list(hidden), append_hidden_shapes=[], base_type=networks.MLPBase,
+               activation_func=torch.nn.ReLU)
+    if kind == "sac":
+        pf = policies.GuassianContPolicy(input_shape=o, output_shape=2 * a, tanh_action=True, **net)
+    else:
+        pf = policies.FixGuassianContPolicy(input_shape=o, output_shape=a, tanh_action=True, norm_std_explore=0.1,
+                                            **net)
+    qf1 = networks.QNet(input_shape=o + a, output_shape=1, **net)
+    qf2 = networks.QNet(input_shape=o + a, output_shape=1, **net)
+    return pf, qf1, qf2
+
+
+class _FakeEnv:
+    def __init__(self, o, a):
+        import gym
+        self.action_space = gym.spaces.Box(-np.ones(a), np.ones(a))
+        self.observation_space = gym.spaces.Box(-np.ones(o), np.ones(o))
+
+
+class _FakeCollector:
+    epoch_frames = 1
+
+
+def _offpolicy_batches(o, a, B, n, seed):
+    rs = np.random.RandomState(seed)
+    return [{"obs": rs.randn(B, o), "next_obs": rs.randn(B, o), "acts": np.tanh(rs.randn(B, a)),
+             "rewards": rs.randn(B, 1), "terminals": (rs.rand(B, 1) < 0.1).astype(np.float64)} for _ in range(n)]
+
+
+@pytest.mark.parametrize("kind", ["sac", "td3"])
+def test_port_reproduces_reference_offpolicy_updates(tmp_path, kind):
+    import torch
+    import torch.nn as nn
+    from oracle import reference_loader, ref_port
+    reference_loader.load()
+    from torchrl.algo import TwinSACQ, TD3
+    o, a, hidden, B, seed = 11, 3, (24, 24), 48, 4
+    batches = _offpolicy_batches(o, a, B, 4, seed)
+    pf, qf1, qf2 = _ref_offpolicy_nets(kind, o, a, hidden, seed)
+    common = dict(env=_FakeEnv(o, a), replay_buffer=None, collector=_FakeCollector(), logger=None, discount=0.99,
+                  batch_size=B, device="cpu", save_dir=str(tmp_path), tau=0.005, use_soft_update=True)
+    if kind == "sac":
+        ref = TwinSACQ(pf=pf, qf1=qf1, qf2=qf2, plr=3e-4, qlr=3e-4, policy_std_reg_weight=1e-3,
+                       policy_mean_reg_weight=1e-3, **common)
+    else:
+        ref = TD3(pf=pf, qf1=qf1, qf2=qf2, plr=1e-3, qlr=1e-3, **common)
+    torch.manual_seed(100)
+    ref_infos = [ref.update(b) for b in batches]
+    ref_params = [p.detach().numpy().copy() for n_ in ref.networks for p in n_.parameters()]
+
+    torch.manual_seed(seed)
+    if kind == "sac":
+        ppf = ref_port.TanhGaussianPolicy(o, a, list(hidden), nn.ReLU, state_dependent_std=True)
+    else:
+        ppf = ref_port.FixedNoisePolicy(o, a, list(hidden), nn.ReLU, norm_std_explore=0.1, tanh_action=True)
+    pq1 = ref_port.QNet(o + a, 1, list(hidden), nn.ReLU)
+    pq2 = ref_port.QNet(o + a, 1, list(hidden), nn.ReLU)
+    if kind == "sac":
+        port = ref_port.SACPort(ppf, pq1, pq2, a, std_reg=1e-3, mean_reg=1e-3)
+        nets = [port.pf, port.qf1, port.qf2, port.tqf1, port.tqf2]
+    else:
+        port = ref_port.TD3Port(ppf, pq1, pq2, plr=1e-3, qlr=1e-3)
+        nets = [port.pf, port.qf1, port.qf2, port.tpf, port.tqf1, port.tqf2]
+    torch.manual_seed(100)
+    port_infos = [port.update(b) for b in batches]
+    port_params = [p.detach().numpy() for n_ in nets for p in n_.parameters()]
+    for x, y in zip(ref_infos, port_infos):
+        assert x.keys() == y.keys()
+        for k in x:
+            assert x[k] == y[k], k
+    assert len(ref_params) == len(port_params)
+    for x, y in zip(ref_params, port_params):
+        np.testing.assert_array_equal(x, y)

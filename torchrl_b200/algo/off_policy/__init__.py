@@ -1,0 +1,3 @@
+from .twin_sac_q import TwinSACQ  # noqa: F401
+from .td3 import TD3  # noqa: F401
+from .dqn import DQN, QRDQN  # noqa: F401

@@ -158,10 +158,14 @@ class RLAlgo:
         raise NotImplementedError
 
     def _update_target_networks(self):
-        """Polyak / periodic hard copy of the target nets (rl_algo.py:169-176) on flat buffers."""
+        """Polyak update of the target nets (rl_algo.py:169-172) on the flat buffers: one launch,
+        captured inside the update graph.  The periodic HARD copy (rl_algo.py:173-176) depends on a
+        host counter, so it is applied by `_maybe_hard_update` outside of any captured graph."""
         if self.use_soft_update:
             ops.polyak_update(self._target_flat.data, self._target_source(), self.tau)
-        elif self.training_update_num % self.target_hard_update_period == 0:
+
+    def _maybe_hard_update(self):
+        if not self.use_soft_update and self.training_update_num % self.target_hard_update_period == 0:
             self._target_flat.data.copy_(self._target_source())
 
     @property

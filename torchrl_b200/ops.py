@@ -274,3 +274,97 @@ def gaussian_log_prob(mean, log_std, actions, tanh_action, out=None):
 def polyak_update(target_flat, source_flat, tau):
     _lib.call("trl_polyak_update", _chk(target_flat, F32, "target"), _chk(source_flat, F32, "source"),
               target_flat.numel(), float(tau), _stream())
+
+
+# ------------------------------------------------------------------------------------------ K10
+class OffPolicyScratch:
+    """Scratch + tickets for the off-policy loss kernels (allocated once per batch size)."""
+
+    def __init__(self, B, device):
+        n = int(_lib.load().trl_offpolicy_scratch_doubles(int(B)))
+        self.buf = [torch.zeros(max(n, 1), dtype=F64, device=device) for _ in range(5)]
+        self.tickets = torch.zeros(8, dtype=I32, device=device)
+        self.B = int(B)
+
+    def t(self, i):
+        return self.tickets[i:i + 1].data_ptr()
+
+
+def td_target(rewards, terminals, q1_next, q2_next, logp_next, log_alpha, gamma, scratch, y=None, info=None,
+              fixed_alpha=1.0):
+    """y = r + (1-d)*gamma*(min(Q1',Q2') - alpha*logpi')  (SAC, twin_sac_q.py:133-139) or the TD3 form
+    (td3.py:86-90) when logp_next is None.  info[0] = mean reward."""
+    B = rewards.numel()
+    if y is None:
+        y = torch.empty(B, dtype=F32, device=rewards.device)
+    if info is None:
+        info = torch.zeros(1, dtype=F32, device=rewards.device)
+    _lib.call("trl_td_target", _chk(rewards, F32, "rewards"), _chk(terminals, U8, "terminals"),
+              _chk(q1_next, F32, "q1_next"), _opt(q2_next, F32, "q2_next"), _opt(logp_next, F32, "logp_next"),
+              _opt(log_alpha, F32, "log_alpha"), float(fixed_alpha), float(gamma), B, _chk(y, F32, "y"),
+              _chk(info, F32, "info"), scratch.buf[0].data_ptr(), scratch.t(0), _stream())
+    return y, info
+
+
+def td3_smooth_action(action, sigma, noise_clip, eps=None, rng=None, out=None):
+    """clamp(a + clamp(sigma*eps, +-c), +-1)  (td3.py:75-84)."""
+    if out is None:
+        out = torch.empty_like(action)
+    seed, ctr = (0, None)
+    if eps is None:
+        seed, ctr = rng.seed, rng.counter
+    _lib.call("trl_td3_smooth_action", _chk(action, F32, "action"), _opt(eps, F32, "eps"), float(sigma),
+              float(noise_clip), ctypes.c_uint64(seed), _opt(ctr, I64, "rng_counter"), action.numel(),
+              _chk(out, F32, "out"), _stream())
+    return out
+
+
+def sac_alpha_step(logp, target_entropy, log_alpha, adam_state, lr, scratch, info=None, betas=(0.9, 0.999), eps=1e-8):
+    """Temperature loss and its Adam step in one launch (twin_sac_q.py:111-123); info = [alpha, alpha_loss]."""
+    if info is None:
+        info = torch.zeros(2, dtype=F32, device=logp.device)
+    _lib.call("trl_sac_alpha_step", _chk(logp, F32, "logp"), float(target_entropy), _chk(log_alpha, F32, "log_alpha"),
+              _chk(adam_state, F32, "adam_state"), float(lr), float(betas[0]), float(betas[1]), float(eps),
+              logp.numel(), _chk(info, F32, "info"), scratch.buf[1].data_ptr(), scratch.t(1), _stream())
+    return info
+
+
+def sac_policy_loss(logp, q1, q2, log_alpha, scratch, info=None, fixed_alpha=1.0):
+    """mean(alpha*logpi - min(q1,q2)) with gradients wrt its three inputs (twin_sac_q.py:145-153)."""
+    B = logp.numel()
+    g_lp, g1, g2 = torch.empty_like(logp), torch.empty_like(q1), torch.empty_like(q2)
+    if info is None:
+        info = torch.zeros(5, dtype=F32, device=logp.device)
+    _lib.call("trl_sac_policy_loss", _chk(logp, F32, "logp"), _chk(q1, F32, "q1"), _chk(q2, F32, "q2"),
+              _opt(log_alpha, F32, "log_alpha"), float(fixed_alpha), B, _chk(g_lp, F32, "g_logp"),
+              _chk(g1, F32, "g_q1"), _chk(g2, F32, "g_q2"), _chk(info, F32, "info"), scratch.buf[2].data_ptr(),
+              scratch.t(2), _stream())
+    return g_lp, g1, g2, info
+
+
+def twin_mse_loss(q1, q2, y, scratch, info=None):
+    """MSE of one or two critics against y: losses in info[0:2], gradients returned (twin_sac_q.py:142-143)."""
+    B = q1.numel()
+    g1 = torch.empty_like(q1)
+    g2 = torch.empty_like(q2) if q2 is not None else None
+    if info is None:
+        info = torch.zeros(2, dtype=F32, device=q1.device)
+    _lib.call("trl_twin_mse_loss", _chk(q1, F32, "q1"), _opt(q2, F32, "q2"), _chk(y, F32, "y"), B,
+              _chk(g1, F32, "g1"), _opt(g2, F32, "g2"), _chk(info, F32, "info"), scratch.buf[3].data_ptr(),
+              scratch.t(3), _stream())
+    return g1, g2, info
+
+
+def qr_dqn_loss(pred, nxt, actions, rewards, terminals, gamma, scratch, n_actions, n_quantiles, mse=False, kappa=1.0,
+                info=None):
+    """Fused (QR-)DQN loss: quantile-Huber (qrdqn.py:36-60, utils.py:5-13) or squared TD error (dqn.py:53-60);
+    returns d loss / d pred with the shape of pred and info = [loss, mean q_s_a, mean reward]."""
+    B = rewards.numel()
+    grad = torch.empty_like(pred)
+    if info is None:
+        info = torch.zeros(3, dtype=F32, device=pred.device)
+    _lib.call("trl_qr_dqn_loss", _chk(pred, F32, "pred"), _chk(nxt, F32, "next"), _chk(actions, F32, "actions"),
+              _chk(rewards, F32, "rewards"), _chk(terminals, U8, "terminals"), B, int(n_actions), int(n_quantiles),
+              float(gamma), float(kappa), int(bool(mse)), _chk(grad, F32, "grad"), _chk(info, F32, "info"),
+              scratch.buf[4].data_ptr(), scratch.t(4), _stream())
+    return grad, info

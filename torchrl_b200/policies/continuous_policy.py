@@ -91,10 +91,10 @@ class FixGuassianContPolicy(networks.Net):
             return {"action": action + noise}
         rng = self._rng.ensure(action.device)
         zero_ls = torch.zeros(action.shape[-1], device=action.device)
-        out = ops.tanh_gaussian_sample(action.detach() if not action.requires_grad else action.detach(), zero_ls,
-                                       tanh_action=False, noise_scale=float(self.norm_std_explore), rng=rng)
+        out = ops.tanh_gaussian_sample(action.detach().contiguous(), zero_ls, tanh_action=False,
+                                       noise_scale=float(self.norm_std_explore), rng=rng)
         ops.counter_advance(rng.counter)
-        noise = out["action"] - action.detach()
+        noise = out["action"] - action.detach()            # sigma * N(0,1), Philox
         return {"action": action + noise}
 
 
