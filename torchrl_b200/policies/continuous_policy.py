@@ -124,6 +124,7 @@ class GuassianContPolicyBase:
         """Sample an action.  Returns the reference's dict: mean, log_std, std, ent, action
         [, log_prob, pre_tanh].  `eps` optionally supplies the N(0,1) noise (tests)."""
         mean, std, log_std = self.forward(x)
+        mean = mean if mean.is_contiguous() else mean.contiguous()
         ls = log_std if log_std.dim() == 1 else log_std.expand_as(mean).contiguous()
         if eps is None and D.get_noise_mode() == "reference_cpu":
             eps = D.draw_reference_noise(tuple(mean.shape), mean.device)
@@ -149,6 +150,7 @@ class GuassianContPolicyBase:
     def act_only(self, x, eps=None, action_out=None, nan_flag=None):
         """Collector fast path: sampled action only (no entropy / dict), one launch after the MLP."""
         mean, _, log_std = self.forward(x)
+        mean = mean if mean.is_contiguous() else mean.contiguous()
         ls = log_std if log_std.dim() == 1 else log_std.expand_as(mean).contiguous()
         rng = self._rng_state(mean.device)
         out = ops.tanh_gaussian_sample(mean, ls, eps=eps, tanh_action=bool(self.tanh_action), rng=rng,
