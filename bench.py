@@ -171,13 +171,44 @@ def auto_procs(env_nums, want=0):
     return max(p, 1), cores
 
 
+def best_torch_threads(cores):
+    """torch intra-op thread count that makes the CPU arm's PPO minibatch fastest on this host.  More
+    threads is not monotonically better (all 128 hyper-threads of the GPU box are ~100x SLOWER than
+    32 for these GEMM sizes), so probe a few counts once and keep the best: the CPU arm gets the most
+    favourable setting, not a pessimised one."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from oracle import ref_port
+    cands = sorted({c for c in (8, 16, 32, 64, cores // 2, cores) if 1 <= c <= cores})
+    B = BATCH_ROWS * N_ENVS_PER_GPU
+    rs = np.random.RandomState(0)
+    batch = {"obs": rs.randn(B, OBS_DIM), "acts": np.tanh(rs.randn(B, ACT_DIM)), "advs": rs.randn(B, 1),
+             "estimate_returns": rs.randn(B, 1), "values": rs.randn(B, 1)}
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        torch.manual_seed(0)
+        agent = ref_port.PPOPort(ref_port.TanhGaussianPolicy(OBS_DIM, ACT_DIM, list(HIDDEN), nn.Tanh),
+                                 ref_port.MLPNet(OBS_DIM, 1, list(HIDDEN), nn.Tanh), None, batch_size=B)
+        agent.update(batch)
+        t0 = time.perf_counter()
+        agent.update(batch)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = c, dt
+        if dt > 4 * best_t:          # past the knee: larger counts only get worse
+            break
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     env_nums = args.envs_per_gpu
     procs, cores = auto_procs(env_nums, args.cpu_procs)
-    threads = cores
+    threads = best_torch_threads(cores)
     vals, ms = [], []
     for i in range(args.warmup + args.steps):
         r = cpu_pipeline_sample(env_nums, procs, sample_steps=4, sample_minibatches=2, threads=threads)
@@ -198,7 +229,8 @@ def run_reference(args):
                                "batch %d, %d opt epochs" % (env_nums, HORIZON, list(HIDDEN), BATCH_ROWS * env_nums,
                                                             OPT_EPOCHS),
                    "parallelism": "cpu: %d env worker processes, %d torch threads" % (procs, threads)},
-        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": max(procs, threads), "host_logical_cores": cores,
+                         "kind": "port", "sample": sample,
                          "detail": {k: last[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s")}},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -375,11 +407,14 @@ def run_ours(args):
     cpu_baseline = None
     if ctx.rank == 0 and args.gpus == 1 and not args.skip_cpu_baseline:
         procs, cores = auto_procs(args.envs_per_gpu, args.cpu_procs)
-        r = cpu_pipeline_sample(args.envs_per_gpu, procs, sample_steps=6, sample_minibatches=3, threads=cores)
-        cpu_baseline = {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": cores, "kind": "port",
+        threads = best_torch_threads(cores)
+        r = cpu_pipeline_sample(args.envs_per_gpu, procs, sample_steps=6, sample_minibatches=3, threads=threads)
+        cpu_baseline = {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": max(procs, threads),
+                        "host_logical_cores": cores, "kind": "port",
                         "sample": "6 collector steps x %d envs over %d spawned env workers + full-horizon Python GAE "
-                                  "+ 3 PPO minibatches of %d samples (%d torch threads); epoch time composed from the "
-                                  "three rates" % (args.envs_per_gpu, procs, BATCH_ROWS * args.envs_per_gpu, cores),
+                                  "+ 3 PPO minibatches of %d samples (%d torch threads = fastest of a probe; host has %d "
+                                  "logical cores); epoch time composed from the three rates"
+                                  % (args.envs_per_gpu, procs, BATCH_ROWS * args.envs_per_gpu, threads, cores),
                         "detail": {k: r[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s", "t_epoch_s")}}
 
     if ctx.rank == 0:
@@ -406,7 +441,17 @@ def run_ours(args):
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
-    ctx.destroy()
+    # teardown: drop the captured graphs (they hold NCCL work) before leaving; with several ranks exit
+    # hard after a final barrier -- destroy_process_group() was observed to hang for minutes when
+    # CUDA graphs that captured NCCL kernels are still alive
+    agent._mb_graph = None
+    col._graphs.clear()
+    torch.cuda.synchronize(device)
+    if ctx.active:
+        ctx.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     return 0
 
 

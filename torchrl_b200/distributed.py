@@ -83,14 +83,17 @@ class DataParallelContext:
         return t
 
     def global_vec_stats(self, x, out):
-        """out[0..3] = mean, unbiased std, max, min of the concatenation of `x` over all ranks."""
+        """out[0..3] = mean, unbiased std, max, min of the concatenation of `x` over all ranks (every
+        rank holds the same number of elements).  Device-only: capturable in a CUDA graph."""
         xd = x.double()
-        mom = torch.stack([xd.sum(), (xd * xd).sum(), torch.tensor(float(x.numel()), dtype=torch.float64,
-                                                                    device=x.device)])
+        mom = torch.stack([xd.sum(), (xd * xd).sum()])
         ext = torch.stack([x.max(), -x.min()]).double()
         self.all_reduce_sum_(mom)
         self.all_reduce_max_(ext)
-        mean, std = combine_moments(mom[0], mom[1], mom[2])
+        n = float(x.numel() * self.world_size)
+        mean = mom[0] / n
+        var = (mom[1] - mom[0] * mean) / (n - 1.0)
+        std = torch.sqrt(torch.clamp(var, min=0.0))
         out.copy_(torch.stack([mean, std, ext[0], -ext[1]]).to(out.dtype))
         return out
 
