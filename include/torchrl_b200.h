@@ -162,6 +162,13 @@ int trl_qr_dqn_loss(const float* pred, const float* next, const float* actions, 
                     const uint8_t* terminals, int B, int n_actions, int n_quantiles, float gamma, float kappa,
                     int mse, float* grad, float* info3, double* scratch, unsigned* ticket, void* stream);
 
+/* ---- MLP epilogues around the cuBLAS GEMMs of MLPBase (networks/base.py:24-44): z <- act(z + b) in place
+ * (act: 0 none, 1 tanh, 2 relu) and its backward g_pre = g * act'(out), dbias = column sums (one launch each). */
+int64_t trl_bias_act_bwd_scratch_floats(int64_t M, int H);
+int trl_bias_act_fwd(float* z, const float* bias, int64_t M, int H, int act, void* stream);
+int trl_bias_act_bwd(const float* grad, const float* out, float* grad_pre, float* dbias, int64_t M, int H,
+                     int act, float* scratch, unsigned* tickets, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -53,6 +53,9 @@ SIGNATURES = {
     "trl_grad_sumsq": [vp, vp, i32, u32, vp, vp, f64, f64, vp, vp, vp],
     "trl_adam_step": [vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp, f32, f32, f32, i32, vp],
     "trl_polyak_update": [vp, vp, i64, f32, vp],
+    "trl_bias_act_bwd_scratch_floats": [i64, i32],
+    "trl_bias_act_fwd": [vp, vp, i64, i32, i32, vp],
+    "trl_bias_act_bwd": [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp],
     "trl_offpolicy_scratch_doubles": [i64],
     "trl_td_target": [vp, vp, vp, vp, vp, vp, f32, f32, i64, vp, vp, vp, vp, vp],
     "trl_td3_smooth_action": [vp, vp, f32, f32, u64, vp, i64, vp, vp],
@@ -62,7 +65,7 @@ SIGNATURES = {
     "trl_qr_dqn_loss": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp],
 }
 _RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles": ctypes.c_int64,
-             "trl_offpolicy_scratch_doubles": ctypes.c_int64}
+             "trl_offpolicy_scratch_doubles": ctypes.c_int64, "trl_bias_act_bwd_scratch_floats": ctypes.c_int64}
 # entry points that return a value rather than an error code
 _VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas",
                 "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")

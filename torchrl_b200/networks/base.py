@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import init as winit
+from . import fused
 
 
 class MLPBase(nn.Module):
@@ -43,8 +44,19 @@ class MLPBase(nn.Module):
             layers.append(self.last_activation_func())
         self.fcs = layers
         self.seq_fcs = nn.Sequential(*layers)
+        # (Linear, activation) pairs eligible for the fused CUDA epilogue (no LayerNorm in between)
+        self._pairs = None
+        if not add_ln and len(layers) % 2 == 0 and all(isinstance(layers[i], nn.Linear) for i in range(0, len(layers), 2)):
+            self._pairs = [(layers[i], layers[i + 1]) for i in range(0, len(layers), 2)]
 
     def forward(self, x):
+        if self._pairs and fused.fused_enabled() and x.is_cuda:
+            for fc, act in self._pairs:
+                if fused.can_fuse(x, fc, act):
+                    x = fused.linear_act(x, fc, fused.ACT_CODES[type(act)])
+                else:
+                    x = act(fc(x))
+            return x
         return self.seq_fcs(x)
 
 
