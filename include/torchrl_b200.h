@@ -168,6 +168,18 @@ int64_t trl_bias_act_bwd_scratch_floats(int64_t M, int H);
 int trl_bias_act_fwd(float* z, const float* bias, int64_t M, int H, int act, void* stream);
 int trl_bias_act_bwd(const float* grad, const float* out, float* grad_pre, float* dbias, int64_t M, int H,
                      int act, float* scratch, unsigned* tickets, void* stream);
+/* x = hi + lo, hi = tf32(x): operand split of the error-compensated 3xTF32 tensor-core GEMM (opt-in). */
+int trl_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream);
+
+/* ---- K9 (prioritised variant): proportional prioritised sampling of replay time rows.
+ * PARITY UNPINNED -- the reference has no prioritised replay; the row-granular
+ * definition follows BaseReplayBuffer.random_batch (replay_buffers/base.py:39-51) and is restated in
+ * oracle/ref_numpy.py:per_sample/per_update.  u: device doubles in [0,1) (host np.random for parity). */
+int trl_per_sample(const float* prio, int size, const double* u, int b, float beta, int64_t* idx,
+                   float* weights, void* stream);
+int trl_per_update(float* prio, const int64_t* idx, const float* td, int b, int n, float alpha, float eps,
+                   float* max_prio, void* stream);
+int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void* stream);
 
 #ifdef __cplusplus
 }

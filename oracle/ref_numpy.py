@@ -250,3 +250,29 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
     bc2 = 1 - beta2 ** step
     denom = np.sqrt(v) / np.sqrt(bc2) + eps
     return p - (lr / bc1) * m / denom, m, v
+
+
+# --------------------------------------------------------------------------- prioritised replay (unpinned)
+def per_sample(prio, size, u, beta):
+    """Stratified proportional sampling of time rows + importance weights.
+
+    PARITY UNPINNED: the reference has no prioritised replay; this is the CPU
+    statement of the definition in torchrl_b200/csrc/prioritized.cu.  prio: (rows,) float32 priorities
+    (already ^alpha); u: (b,) uniforms in [0,1).  Returns (idx int64 (b,), weights float64 (b,))."""
+    p = np.asarray(prio[:size], dtype=np.float64)
+    pre = np.cumsum(p)
+    total = pre[-1]
+    b = len(u)
+    target = (np.arange(b, dtype=np.float64) + np.asarray(u, dtype=np.float64)) / b * total
+    idx = np.searchsorted(pre, target, side="right")
+    idx = np.minimum(idx, size - 1)
+    max_w = (size * p.min() / total) ** (-beta)
+    w = (size * p[idx] / total) ** (-beta) / max_w
+    return idx.astype(np.int64), w
+
+
+def per_update(prio, idx, td, alpha, eps, max_prio):
+    """prio[idx_k] = (mean_n |td[k,n]| + eps)^alpha; returns the new running maximum priority."""
+    new = (np.abs(np.asarray(td, dtype=np.float64)).mean(axis=1).astype(np.float32) + np.float32(eps)) ** np.float32(alpha)
+    prio[idx] = new
+    return max(float(max_prio), float(new.max()))

@@ -47,3 +47,57 @@ def test_fused_path_handles_leading_dims_and_no_grad():
         y = net(x)
     assert y.shape == (1, 40, 32)
     torch.testing.assert_close(y, net.seq_fcs(x), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_tf32x3_matmul_is_fp32_faithful():
+    """Error-compensated 3xTF32 GEMM vs float64: its error must be of the order of the fp32 SIMT GEMM's own
+    error (and ~1000x smaller than plain TF32)."""
+    import torch
+    from torchrl_b200.networks import fused
+    torch.manual_seed(0)
+    a = torch.randn(4096, 256, device="cuda")
+    b = torch.randn(256, 256, device="cuda") / 16
+    ref = (a.double() @ b.double())
+    a_hi, a_lo = fused.split_tf32(a)
+    b_hi, b_lo = fused.split_tf32(b)
+    torch.testing.assert_close(a_hi + a_lo, a, rtol=0, atol=0)             # exact split
+    assert (a_hi.view(torch.int32) & 0x1FFF).abs().max().item() == 0          # hi is TF32-representable
+    out3 = fused.mm3(a_hi, a_lo, b_hi, b_lo).double()
+    out32 = (a @ b).double()
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out_tf32 = (a @ b).double()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = False
+    scale = ref.abs().max().item()
+    e3, e32, e1 = ((o - ref).abs().max().item() / scale for o in (out3, out32, out_tf32))
+    print("max rel err: 3xTF32 %.2e  fp32 %.2e  TF32 %.2e" % (e3, e32, e1))
+    assert e3 < 4 * e32 + 1e-7 and e3 < e1 / 50
+
+
+@pytest.mark.gpu
+def test_tf32x3_mlp_matches_fp32_mlp():
+    import copy
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    from torchrl_b200.networks import fused
+    torch.manual_seed(1)
+    net = networks.Net(input_shape=17, output_shape=6, hidden_shapes=[256, 256], append_hidden_shapes=[],
+                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+    ref = copy.deepcopy(net)
+    x = torch.randn(16384, 17, device="cuda")
+    w = torch.randn(16384, 6, device="cuda")
+    fused.set_matmul_mode("tf32x3")
+    try:
+        y1 = net(x)
+        (y1 * w).sum().backward()
+    finally:
+        fused.set_matmul_mode("fp32")
+    y0 = ref(x)
+    (y0 * w).sum().backward()
+    torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
+    for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
+        scale = p0.grad.abs().max().item() + 1e-12
+        torch.testing.assert_close(p1.grad, p0.grad, rtol=1e-4, atol=2e-5 * scale, msg=n1)

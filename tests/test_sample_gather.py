@@ -128,3 +128,71 @@ def test_vec_stats():
     x = torch.randn(16384, device="cuda") * 3 + 1
     st = ops.vec_stats(x).cpu().numpy()
     np.testing.assert_allclose(st, [x.mean().item(), x.std().item(), x.max().item(), x.min().item()], rtol=1e-5)
+
+
+def test_per_oracle_properties():
+    """CPU: the NumPy definition of prioritised row sampling behaves like proportional sampling."""
+    rs = np.random.RandomState(0)
+    prio = rs.rand(500).astype(np.float32) + 0.01
+    counts = np.zeros(500)
+    for _ in range(400):
+        idx, w = rn.per_sample(prio, 500, rs.rand(64), 0.4)
+        assert idx.min() >= 0 and idx.max() < 500 and np.all(np.diff(idx) >= 0)     # stratified => sorted
+        assert w.max() <= 1.0 + 1e-12
+        np.add.at(counts, idx, 1)
+    corr = np.corrcoef(counts, prio)[0, 1]
+    assert corr > 0.9
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size,b", [(1953, 4), (976, 64), (7, 3), (4096, 256)])
+def test_prioritized_sampling_matches_oracle(size, b):
+    import torch
+    from torchrl_b200 import ops
+    rs = np.random.RandomState(size)
+    rows = max(size, 8)
+    prio = (rs.rand(rows).astype(np.float32) + 1e-3) ** 0.6
+    u = rs.rand(b)
+    idx, w = ops.per_sample(torch.from_numpy(prio).cuda(), size, torch.from_numpy(u).cuda(), 0.4)
+    e_idx, e_w = rn.per_sample(prio, size, u, 0.4)
+    np.testing.assert_array_equal(idx.cpu().numpy(), e_idx)          # bit-exact indices
+    np.testing.assert_allclose(w.cpu().numpy(), e_w, rtol=1e-5)
+    # priority update from TD errors + running maximum
+    td = rs.randn(b, 16).astype(np.float32)
+    p_dev = torch.from_numpy(prio.copy()).cuda()
+    mx = torch.ones(1, device="cuda")
+    uniq = np.unique(e_idx, return_index=True)[1]                     # duplicates: last-writer unordered on GPU
+    ops.per_update(p_dev, idx, torch.from_numpy(td).cuda(), 0.6, 1e-6, mx)
+    p_ref = prio.copy()
+    e_max = rn.per_update(p_ref, e_idx, td, 0.6, 1e-6, 1.0)
+    sel = e_idx[np.array([k for k in range(b) if (e_idx == e_idx[k]).sum() == 1], dtype=int)] if b > 1 else e_idx
+    np.testing.assert_allclose(p_dev.cpu().numpy()[sel], p_ref[sel], rtol=1e-5)
+    assert abs(mx.item() - e_max) < 1e-5 * max(1.0, e_max)
+
+
+@pytest.mark.gpu
+def test_prioritized_buffer_api():
+    import torch
+    from torchrl_b200.replay_buffers import PrioritizedReplayBuffer
+    N, o, T = 8, 5, 32
+    buf = PrioritizedReplayBuffer(T * N, env_nums=N, device="cuda", alpha=0.6, beta=0.4)
+    for t in range(20):
+        buf.add_sample({"obs": torch.full((N, o), float(t), device="cuda"),
+                        "rewards": torch.zeros(N, 1, device="cuda"),
+                        "terminals": torch.zeros(N, 1, dtype=torch.bool, device="cuda")})
+    assert torch.all(buf._priorities[:20] == 1.0) and torch.all(buf._priorities[20:] == 0.0)
+    np.random.seed(1)
+    batch = buf.random_batch(4 * N, ["obs", "rewards"])
+    assert batch["obs"].shape == (4 * N, o) and batch["weights"].shape == (4 * N, 1) and batch["indices"].shape == (4,)
+    rows = batch["indices"].cpu().numpy()
+    np.testing.assert_array_equal(batch["obs"].cpu().numpy()[::N, 0], rows.astype(np.float32))
+    assert torch.allclose(batch["weights"], torch.ones_like(batch["weights"]))   # equal priorities -> weights 1
+    td = torch.zeros(4 * N, 1, device="cuda")
+    td[:N] = 10.0                                                               # first sampled row: large TD error
+    buf.update_priorities(batch["indices"], td)
+    assert buf._priorities[rows[0]].item() > 3.9 and abs(buf._max_prio.item() - (10 + 1e-6) ** 0.6) < 1e-4
+    np.random.seed(2)
+    hits = 0
+    for _ in range(50):
+        hits += int((buf.random_batch(4 * N, ["obs"])["indices"] == int(rows[0])).any().item())
+    assert hits >= 25                                                           # high-priority row is drawn often

@@ -55,7 +55,11 @@ SIGNATURES = {
     "trl_polyak_update": [vp, vp, i64, f32, vp],
     "trl_bias_act_bwd_scratch_floats": [i64, i32],
     "trl_bias_act_fwd": [vp, vp, i64, i32, i32, vp],
+    "trl_split_tf32": [vp, i64, vp, vp, vp],
     "trl_bias_act_bwd": [vp, vp, vp, vp, i64, i32, i32, vp, vp, vp],
+    "trl_per_sample": [vp, i32, vp, i32, f32, vp, vp, vp],
+    "trl_per_update": [vp, vp, vp, i32, i32, f32, f32, vp, vp],
+    "trl_per_insert": [vp, vp, vp, vp],
     "trl_offpolicy_scratch_doubles": [i64],
     "trl_td_target": [vp, vp, vp, vp, vp, vp, f32, f32, i64, vp, vp, vp, vp, vp],
     "trl_td3_smooth_action": [vp, vp, f32, f32, u64, vp, i64, vp, vp],

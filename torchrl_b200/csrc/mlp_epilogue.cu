@@ -52,7 +52,7 @@ __global__ void bias_act_fwd_scalar_kernel(float* __restrict__ z, const float* _
 // CTA = 256 threads = 8 row-groups x 32 column-lanes(x4 floats): covers 128 columns x ROWS_PER_CTA rows.
 // Column sums: per-thread accumulation over its rows -> smem across the 8 row-groups -> per-CTA partial
 // -> last CTA of each column block reduces the partials in fixed order (deterministic).
-constexpr int kBwdRows = 256;   // rows per CTA
+constexpr int kBwdRows = 128;   // rows per CTA (M=16384,H=256 -> 256 CTAs)
 
 __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* g, const float* __restrict__ y, float* gz,
                                                           float* __restrict__ db, float* __restrict__ partial,
@@ -92,13 +92,26 @@ __global__ void __launch_bounds__(256) bias_act_bwd_kernel(const float* g, const
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (rg == 0 && col_ok) {
+  // last CTA of this column block: all 8 row-groups share the partial rows (fixed assignment and fixed
+  // combination order -> deterministic), instead of one row-group walking all of them serially
+  {
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (unsigned by = 0; by < gridDim.y; ++by) {
-      const float4 p = *reinterpret_cast<const float4*>(partial + static_cast<long long>(by) * H + col);
-      s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+    if (col_ok) {
+#pragma unroll 4
+      for (unsigned by = rg; by < gridDim.y; by += 8) {
+        const float4 p = *reinterpret_cast<const float4*>(partial + static_cast<long long>(by) * H + col);
+        s.x += p.x; s.y += p.y; s.z += p.z; s.w += p.w;
+      }
     }
-    *reinterpret_cast<float4*>(db + col) = s;
+    __syncthreads();
+    sh[rg][lane] = s;
+    __syncthreads();
+    if (rg == 0 && col_ok) {
+      float4 t = sh[0][lane];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) { t.x += sh[k][lane].x; t.y += sh[k][lane].y; t.z += sh[k][lane].z; t.w += sh[k][lane].w; }
+      *reinterpret_cast<float4*>(db + col) = t;
+    }
   }
   if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
 }
@@ -140,4 +153,66 @@ TRL_API int trl_bias_act_bwd(const float* grad, const float* out, float* grad_pr
   bias_act_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(grad, out, grad_pre, dbias, scratch, tickets,
                                                                           M, H, act);
   return check_launch("bias_act_bwd_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Error-compensated TF32 ("3xTF32") operand split: x = hi + lo with hi = x rounded to TF32 (10-bit
+// mantissa, cvt.rna) and lo = x - hi (exact in fp32).  A fp32-faithful product on the tensor cores is
+// then a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (three TF32 GEMMs with fp32 accumulation; the dropped lo*lo
+// term is O(2^-22) relative).  HBM-bound: 4 B read + 8 B written per element.
+namespace trl {
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                        float* __restrict__ lo, long long n4, long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    float4 h, l;
+    unsigned u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[i] = h;
+    reinterpret_cast<float4*>(lo)[i] = l;
+  }
+  // tail (n not a multiple of 4)
+  const long long t = n4 * 4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (t < n) {
+    unsigned u;
+    const float v = x[t];
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    hi[t] = __uint_as_float(u);
+    lo[t] = v - __uint_as_float(u);
+  }
+}
+__global__ void split_tf32_scalar_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo,
+                                         long long n) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    unsigned u;
+    const float v = x[i];
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    hi[i] = __uint_as_float(u);
+    lo[i] = v - __uint_as_float(u);
+  }
+}
+}  // namespace trl
+
+TRL_API int trl_split_tf32(const float* x, int64_t n, float* hi, float* lo, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(n >= 0, "trl_split_tf32: negative size");
+  if (n == 0) return TRL_OK;
+  TRL_REQUIRE(x && hi && lo, "trl_split_tf32: null pointer");
+  if (!(aligned16(x) && aligned16(hi) && aligned16(lo))) {   // e.g. a weight view into the flat parameter buffer
+    long long sb = ceil_div<long long>(n, 256);
+    if (sb > 8LL * kNumSM) sb = 8LL * kNumSM;
+    split_tf32_scalar_kernel<<<static_cast<unsigned>(sb), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, hi, lo, n);
+    return check_launch("split_tf32_scalar_kernel");
+  }
+  const long long n4 = n / 4;
+  long long blocks = ceil_div<long long>(n4 + 1, 256);
+  if (blocks > 8LL * kNumSM) blocks = 8LL * kNumSM;
+  if (blocks < 1) blocks = 1;
+  split_tf32_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, hi, lo, n4, n);
+  return check_launch("split_tf32_kernel");
 }

@@ -70,8 +70,6 @@ __device__ __forceinline__ float block_reduce_max(float v, float* sh) {
 }
 
 __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const ActorParams p) {
-  __shared__ double shd[32];
-  __shared__ float shf[32];
   __shared__ unsigned s_last;
   const long long b = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool ok = b < p.B;
@@ -114,7 +112,12 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
   }
 
   double* pp = p.partial + static_cast<long long>(blockIdx.x) * (kActorFixed + a);
-  double r;
+  // One block-wide reduction for everything: warp shuffles, per-warp results in shared memory, ONE barrier,
+  // then thread k folds the warps' values of quantity k (previously 18 separate two-barrier reductions).
+  __shared__ double sh_sum[kLossThreads / 32][6 + kMaxAct];
+  __shared__ float sh_max[kLossThreads / 32][6];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int NW = kLossThreads / 32;
   // ---- gradients: second pass over the action dims (values re-read from L1) -------------
   for (int j = 0; j < a; ++j) {
     float gl = 0.f;
@@ -130,25 +133,44 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
       if (p.ls_stride) p.g_log_std[b * a + j] = gl - p.ent_coef * invB;  // entropy: d ent_b/d ls = 1
     }
     if (!p.ls_stride) {
-      r = block_reduce_sum(static_cast<double>(gl), shd);
-      if (threadIdx.x == 0) pp[kActorFixed + j] = r;
+      const double w = warp_sum(static_cast<double>(gl));
+      if (lane == 0) sh_sum[wid][6 + j] = w;
     }
   }
-
-  // ---- CTA partials ------------------------------------------------------------------
-  r = block_reduce_sum(static_cast<double>(Lb), shd);               if (threadIdx.x == 0) pp[0] = r;
-  r = block_reduce_sum(ok ? static_cast<double>(logp) : 0.0, shd);  if (threadIdx.x == 0) pp[1] = r;
-  r = block_reduce_sum(ok ? static_cast<double>(logp) * logp : 0.0, shd); if (threadIdx.x == 0) pp[2] = r;
-  float f;
-  f = block_reduce_max(ok ? logp : -INFINITY, shf);   if (threadIdx.x == 0) pp[3] = f;
-  f = block_reduce_max(ok ? -logp : -INFINITY, shf);  if (threadIdx.x == 0) pp[4] = -f;
-  f = block_reduce_max(ok ? ratio : -INFINITY, shf);  if (threadIdx.x == 0) pp[5] = f;
-  f = block_reduce_max(ok ? -ratio : -INFINITY, shf); if (threadIdx.x == 0) pp[6] = -f;
-  r = block_reduce_sum(static_cast<double>(ls_s), shd);  if (threadIdx.x == 0) pp[7] = r;
-  r = block_reduce_sum(static_cast<double>(ls_q), shd);  if (threadIdx.x == 0) pp[8] = r;
-  f = block_reduce_max(ls_mx, shf);                      if (threadIdx.x == 0) pp[9] = f;
-  f = block_reduce_max(-ls_mn, shf);                     if (threadIdx.x == 0) pp[10] = -f;
-  r = block_reduce_sum(static_cast<double>(dkl), shd);   if (threadIdx.x == 0) pp[11] = r;
+  {
+    const double sums[6] = {static_cast<double>(Lb), ok ? static_cast<double>(logp) : 0.0,
+                            ok ? static_cast<double>(logp) * logp : 0.0, static_cast<double>(ls_s),
+                            static_cast<double>(ls_q), static_cast<double>(dkl)};
+    const float maxs[6] = {ok ? logp : -INFINITY, ok ? -logp : -INFINITY, ok ? ratio : -INFINITY,
+                           ok ? -ratio : -INFINITY, ls_mx, -ls_mn};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const double w = warp_sum(sums[k]);
+      const float m = warp_max(maxs[k]);
+      if (lane == 0) { sh_sum[wid][k] = w; sh_max[wid][k] = m; }
+    }
+  }
+  __syncthreads();
+  {
+    const int k = threadIdx.x;
+    const int nsum = 6 + (p.ls_stride ? 0 : a);
+    if (k < nsum) {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += sh_sum[w][k];
+      // partial slots: 0 L, 1 logp, 2 logp^2, 7 ls, 8 ls^2, 11 dkl, 12+j dL/dls_j
+      const int slot = k == 0 ? 0 : k == 1 ? 1 : k == 2 ? 2 : k == 3 ? 7 : k == 4 ? 8 : k == 5 ? 11 : kActorFixed + (k - 6);
+      pp[slot] = t;
+    } else if (k >= 32 && k < 38) {
+      const int q = k - 32;
+      float m = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) m = fmaxf(m, sh_max[w][q]);
+      // 3 max logp, 4 min logp, 5 max ratio, 6 min ratio, 9 max ls, 10 min ls
+      const int slot = q == 0 ? 3 : q == 1 ? 4 : q == 2 ? 5 : q == 3 ? 6 : q == 4 ? 9 : 10;
+      pp[slot] = (q & 1) ? -static_cast<double>(m) : static_cast<double>(m);
+    }
+  }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -156,17 +178,29 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
   if (!s_last) return;
   __threadfence();
   // ---- last CTA: fixed-order reduction of the partials ----------------------------------
-  const int K = kActorFixed + a;
+  const int K = kActorFixed + a;   // <= 44
   const int nb = gridDim.x;
-  if (threadIdx.x < K) {
-    const int k = threadIdx.x;
+  // 4 chunks x 64 quantity slots: thread (chunk, k) folds partials i = chunk, chunk+4, ... ; fixed order
+  __shared__ double sh_fin[4][64];
+  {
+    const int k = threadIdx.x & 63, chunk = threadIdx.x >> 6;
     const bool is_max = (k == 3 || k == 5 || k == 9), is_min = (k == 4 || k == 6 || k == 10);
     double acc = is_max ? -INFINITY : (is_min ? INFINITY : 0.0);
-    for (int i = 0; i < nb; ++i) {
-      const double v = p.partial[static_cast<long long>(i) * K + k];
-      acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+    if (k < K) {
+      for (int i = chunk; i < nb; i += 4) {
+        const double v = p.partial[static_cast<long long>(i) * K + k];
+        acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+      }
     }
-    p.partial[k] = acc;  // slot 0 now holds the totals (all other CTAs are done)
+    sh_fin[chunk][k] = acc;
+    __syncthreads();
+    if (chunk == 0 && k < K) {
+      for (int c = 1; c < 4; ++c) {
+        const double v = sh_fin[c][k];
+        acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+      }
+      p.partial[k] = acc;  // slot 0 now holds the totals (all other CTAs are done)
+    }
   }
   __syncthreads();
   if (threadIdx.x == 0) {

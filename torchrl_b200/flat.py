@@ -29,18 +29,24 @@ class FlatParams:
         plist = [p for seg in self.segments for p in seg]
         assert plist, "no parameters"
         self.device = torch.device(device) if device is not None else plist[0].device
-        sizes = [sum(p.numel() for p in seg) for seg in self.segments]
+        # every parameter starts on a 16-byte boundary (4 floats) so kernels can use float4 on weight /
+        # bias views; the padding elements are zero, receive zero gradient and stay zero under Adam
+        self.offsets = []
         self.seg_begin = [0]
-        for s in sizes:
-            self.seg_begin.append(self.seg_begin[-1] + s)
-        self.total = self.seg_begin[-1]
-        self.data = torch.empty(self.total, dtype=F32, device=self.device)
         off = 0
-        for p in plist:
+        for seg in self.segments:
+            for p in seg:
+                off = (off + 3) // 4 * 4
+                self.offsets.append(off)
+                off += p.numel()
+            off = (off + 3) // 4 * 4
+            self.seg_begin.append(off)
+        self.total = self.seg_begin[-1]
+        self.data = torch.zeros(self.total, dtype=F32, device=self.device)
+        for p, o in zip(plist, self.offsets):
             n = p.numel()
-            self.data[off:off + n].copy_(p.data.reshape(-1))
-            p.data = self.data[off:off + n].view(p.shape)
-            off += n
+            self.data[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.data[o:o + n].view(p.shape)
         self.params = plist
 
     def seg_slice(self, i, j=None):
@@ -60,11 +66,8 @@ class FlatAdam(FlatParams):
         self.grad = torch.zeros(self.total, dtype=F32, device=self.device)
         self.exp_avg = torch.zeros(self.total, dtype=F32, device=self.device)
         self.exp_avg_sq = torch.zeros(self.total, dtype=F32, device=self.device)
-        off = 0
-        for p in self.params:
-            k = p.numel()
-            p.grad = self.grad[off:off + k].view(p.shape)
-            off += k
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
         lrs = [float(x) for x in (lrs if isinstance(lrs, (list, tuple)) else [lrs] * n)]
         eps = [float(x) for x in (eps if isinstance(eps, (list, tuple)) else [eps] * n)]
         if max_norms is None:

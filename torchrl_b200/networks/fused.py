@@ -14,6 +14,62 @@ from .. import _lib, ops
 
 ACT_CODES = {nn.Tanh: 1, nn.ReLU: 2}
 _ENABLED = True
+_MATMUL_MODE = "fp32"            # "fp32": cuBLAS SIMT sgemm | "tf32x3": error-compensated tensor-core GEMMs
+_TF32X3_MIN_DIM = 64             # layers narrower than this stay on the plain path
+
+
+def set_matmul_mode(mode):
+    """"fp32" (default) or "tf32x3": x@w computed as x_hi@w_hi + x_lo@w_hi + x_hi@w_lo on the TF32 tensor
+    cores with fp32 accumulation (operands split by csrc/mlp_epilogue.cu:split_tf32_kernel) -- fp32-faithful
+    results (the dropped lo*lo term is O(2^-22)), unlike plain TF32."""
+    global _MATMUL_MODE
+    assert mode in ("fp32", "tf32x3")
+    _MATMUL_MODE = mode
+
+
+def get_matmul_mode():
+    return _MATMUL_MODE
+
+
+def split_tf32(t):
+    """(hi, lo) of a contiguous fp32 tensor."""
+    hi, lo = torch.empty_like(t), torch.empty_like(t)
+    _lib.call("trl_split_tf32", ops._chk(t, torch.float32, "x"), t.numel(), hi.data_ptr(), lo.data_ptr(),
+              ops._stream())
+    return hi, lo
+
+
+def wgrad(gz, x):
+    """dW = gz^T @ x  for gz (M,H), x (M,K): split-K batched GEMM + partial sum.
+
+    The direct `mm(gz.t(), x)` lands on a slow cuBLAS `nt` kernel for this shape class (tiny output, K =
+    minibatch): measured on B200 at M=16384: (256x256) 104 us -> 52 us, (256x17) 54 -> 19 us, (6x256) 27 -> 17 us
+    (gpurun_out/wgrad_probe.txt, scripts/wgrad_probe.py).  Splitting the reduction over S slabs exposes S x more
+    CTAs; the S partial products are summed in a fixed order (deterministic)."""
+    M, H = gz.shape
+    K = x.shape[1]
+    if H < 4 or M < 4096:
+        return torch.mm(gz.t(), x)
+    S = 16 if min(H, K) >= 128 else 64
+    while S > 1 and M % S:
+        S //= 2
+    if S == 1:
+        return torch.mm(gz.t(), x)
+    m = M // S
+    return torch.bmm(gz.view(S, m, H).transpose(1, 2), x.view(S, m, K)).sum(0)
+
+
+def mm3(a_hi, a_lo, b_hi, b_lo):
+    """a@b from pre-split operands: three TF32 tensor-core GEMMs accumulated in fp32."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = torch.mm(a_lo, b_hi)
+        out.addmm_(a_hi, b_lo)
+        out.addmm_(a_hi, b_hi)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return out
 
 
 def set_fused_epilogue(flag):
@@ -45,15 +101,25 @@ class _Workspace:
 class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
-        z = torch.mm(x, weight.t())
+        tc = (_MATMUL_MODE == "tf32x3" and min(x.shape[0], x.shape[1], weight.shape[0]) >= _TF32X3_MIN_DIM)
+        if tc:
+            x_hi, x_lo = split_tf32(x)
+            w_hi, w_lo = split_tf32(weight)
+            z = mm3(x_hi, x_lo, w_hi.t(), w_lo.t())
+            ctx.save_for_backward(x_hi, x_lo, w_hi, w_lo, z)
+        else:
+            z = torch.mm(x, weight.t())
+            ctx.save_for_backward(x, weight, z)
         _lib.call("trl_bias_act_fwd", z.data_ptr(), ops._chk(bias, torch.float32, "bias"), z.shape[0], z.shape[1],
                   act, ops._stream())
-        ctx.save_for_backward(x, weight, z)
         ctx.act = act
+        ctx.tc = tc
         return z
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.tc:
+            return _LinearAct._backward_tc(ctx, g)
         x, weight, y = ctx.saved_tensors
         g = g if g.is_contiguous() else g.contiguous()
         M, H = y.shape
@@ -63,8 +129,53 @@ class _LinearAct(torch.autograd.Function):
         _lib.call("trl_bias_act_bwd", g.data_ptr(), y.data_ptr(), gz.data_ptr(), db.data_ptr(), M, H, ctx.act,
                   scratch.data_ptr(), tickets.data_ptr(), ops._stream())
         dx = torch.mm(gz, weight) if ctx.needs_input_grad[0] else None
-        dw = torch.mm(gz.t(), x) if ctx.needs_input_grad[1] else None
+        dw = wgrad(gz, x) if ctx.needs_input_grad[1] else None
         return dx, dw, (db if ctx.needs_input_grad[2] else None), None
+
+
+def _backward_tc(ctx, g):
+    x_hi, x_lo, w_hi, w_lo, y = ctx.saved_tensors
+    g = g if g.is_contiguous() else g.contiguous()
+    M, H = y.shape
+    gz = torch.empty_like(y)
+    db = torch.empty(H, dtype=torch.float32, device=y.device)
+    scratch, tickets = _Workspace.get(M, H, y.device)
+    _lib.call("trl_bias_act_bwd", g.data_ptr(), y.data_ptr(), gz.data_ptr(), db.data_ptr(), M, H, ctx.act,
+              scratch.data_ptr(), tickets.data_ptr(), ops._stream())
+    g_hi, g_lo = split_tf32(gz)
+    dx = mm3(g_hi, g_lo, w_hi, w_lo) if ctx.needs_input_grad[0] else None
+    dw = mm3(g_hi.t(), g_lo.t(), x_hi, x_lo) if ctx.needs_input_grad[1] else None
+    return dx, dw, (db if ctx.needs_input_grad[2] else None), None
+
+
+_LinearAct._backward_tc = staticmethod(_backward_tc)
+
+
+class _LinearPlain(torch.autograd.Function):
+    """Linear without activation (the output layer of Net): cuBLAS forward, split-K wgrad backward."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return torch.addmm(bias, x, weight.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g if g.is_contiguous() else g.contiguous()
+        dx = torch.mm(g, weight) if ctx.needs_input_grad[0] else None
+        dw = wgrad(g, x) if ctx.needs_input_grad[1] else None
+        db = g.sum(0) if ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
+def linear_plain(x, fc):
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    out = _LinearPlain.apply(x2, fc.weight, fc.bias)
+    return out.reshape(tuple(lead) + (out.shape[-1],))
 
 
 def linear_act(x, fc, act_code):

@@ -4,6 +4,7 @@ import torch
 import torch.nn as nn
 
 from . import init as winit
+from . import fused
 
 
 class ZeroNet(nn.Module):
@@ -39,8 +40,14 @@ class Net(nn.Module):
                                         add_ln, append_hidden_init_func, net_last_init_func)
         self.seq_append_fcs = nn.Sequential(*self.append_fcs)
 
+    def _head(self, h):
+        if (len(self.append_fcs) == 1 and fused.fused_enabled() and h.is_cuda and h.dtype == torch.float32
+                and torch.is_grad_enabled()):
+            return fused.linear_plain(h, self.append_fcs[0])
+        return self.seq_append_fcs(h)
+
     def forward(self, x):
-        return self.seq_append_fcs(self.base(x))
+        return self._head(self.base(x))
 
 
 class FlattenNet(Net):
@@ -54,7 +61,7 @@ class QNet(Net):
     def forward(self, input):
         assert len(input) == 2, "Q Net only get observation and action"
         state, action = input
-        return self.seq_append_fcs(self.base(torch.cat([state, action], dim=-1)))
+        return self._head(self.base(torch.cat([state, action], dim=-1)))
 
 
 class BootstrappedNet(nn.Module):

@@ -368,3 +368,29 @@ def qr_dqn_loss(pred, nxt, actions, rewards, terminals, gamma, scratch, n_action
               float(gamma), float(kappa), int(bool(mse)), _chk(grad, F32, "grad"), _chk(info, F32, "info"),
               scratch.buf[4].data_ptr(), scratch.t(4), _stream())
     return grad, info
+
+
+# ------------------------------------------------------------------------------------------ K9 prioritised
+def per_sample(prio, size, u, beta, idx=None, weights=None):
+    """Stratified proportional row sampling + importance weights (csrc/prioritized.cu; parity unpinned)."""
+    b = u.numel()
+    if idx is None:
+        idx = torch.empty(b, dtype=I64, device=prio.device)
+    if weights is None:
+        weights = torch.empty(b, dtype=F32, device=prio.device)
+    _lib.call("trl_per_sample", _chk(prio, F32, "prio"), int(size), _chk(u, F64, "u"), b, float(beta),
+              _chk(idx, I64, "idx"), _chk(weights, F32, "weights"), _stream())
+    return idx, weights
+
+
+def per_update(prio, idx, td, alpha, eps, max_prio):
+    """prio[idx_k] = (mean_n |td[k,n]| + eps)^alpha and running max priority."""
+    b = idx.numel()
+    n = td.numel() // b
+    _lib.call("trl_per_update", _chk(prio, F32, "prio"), _chk(idx, I64, "idx"), _chk(td, F32, "td"), b, n,
+              float(alpha), float(eps), _chk(max_prio, F32, "max_prio"), _stream())
+
+
+def per_insert(prio, row_ptr, max_prio):
+    _lib.call("trl_per_insert", _chk(prio, F32, "prio"), _chk(row_ptr, I32, "row_ptr"), _chk(max_prio, F32, "max_prio"),
+              _stream())
