@@ -155,11 +155,30 @@ __global__ void __launch_bounds__(kEnvThreads) synth_env_step_kernel(const EnvPa
     __syncthreads();
     if (s_last) {
       __threadfence();
+      // fold the per-CTA partials with all threads: thread (part, c) sums CTAs b = part, part+P, ... of
+      // column c (c < 2*o), then `part` results are combined in fixed order (deterministic); the previous
+      // version walked all CTAs serially in `o` threads and dominated the kernel's latency
+      double* sred = reinterpret_cast<double*>(sm);          // tile memory is dead by now: reuse as scratch
+      const int C = 2 * o;
+      const int P = nthr / C > 0 ? (nthr / C < 8 ? nthr / C : 8) : 1;
+      if (C <= nthr) {
+        const int part = tid / C, c = tid - part * C;
+        if (part < P) {
+          double acc = 0.0;
+          for (unsigned b = part; b < gridDim.x; b += P) acc += p.partial[static_cast<long long>(b) * C + c];
+          sred[part * C + c] = acc;
+        }
+      }
+      __syncthreads();
       for (int j = tid; j < o; j += nthr) {
         double s = 0.0, q = 0.0;
-        for (unsigned b = 0; b < gridDim.x; ++b) {  // fixed order -> deterministic
-          s += p.partial[static_cast<long long>(b) * 2 * o + j];
-          q += p.partial[static_cast<long long>(b) * 2 * o + o + j];
+        if (C <= nthr) {
+          for (int part = 0; part < P; ++part) { s += sred[part * C + j]; q += sred[part * C + o + j]; }
+        } else {
+          for (unsigned b = 0; b < gridDim.x; ++b) {
+            s += p.partial[static_cast<long long>(b) * C + j];
+            q += p.partial[static_cast<long long>(b) * C + o + j];
+          }
         }
         if (p.batch_sums) { p.batch_sums[j] = s; p.batch_sums[o + j] = q; }
         if (p.merge) {
