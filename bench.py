@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0, help="env worker processes of the CPU arm (0 = auto)")
-    ap.add_argument("--matmul", default="fp32", choices=["fp32", "tf32x3"],
-                    help="MLP GEMM path: fp32 cuBLAS SIMT (default) or error-compensated 3xTF32 tensor cores")
+    ap.add_argument("--matmul", default="tc3", choices=["fp32", "tf32x3", "tc3"],
+                    help="MLP GEMM path: tc3 = hand-written tcgen05 3xTF32 kernel on the 256-wide layers (default), fp32 = cuBLAS SIMT everywhere, tf32x3 = 3 cuBLAS TF32 GEMMs")
     return ap.parse_args()
 
 
@@ -436,8 +436,10 @@ def run_ours(args):
                                       BATCH_ROWS * args.envs_per_gpu, OPT_EPOCHS, 1 if ctx.world_size == 1 else 4),
                        "global_envs": args.envs_per_gpu * ctx.world_size,
                        "parallelism": "dp%d (env sharding, NCCL all-reduce of the flat gradient)" % ctx.world_size,
-                       "matmul": "fp32 cuBLAS SIMT (TF32 off)" if args.matmul == "fp32" else
-                       "3xTF32 error-compensated tensor-core GEMMs (fp32-faithful), cuBLAS", "cuda_graphs": not args.no_graph,
+                       "matmul": {"fp32": "fp32 cuBLAS SIMT (TF32 off)",
+                                  "tf32x3": "3xTF32 error-compensated tensor-core GEMMs (fp32-faithful), cuBLAS",
+                                  "tc3": "256-wide layers: hand-written tcgen05 3xTF32 GEMM (fp32-faithful, "
+                                         "csrc/gemm_tf32x3.cu); other layers fp32 cuBLAS SIMT"}[args.matmul], "cuda_graphs": not args.no_graph,
                        "l2": "each step rewrites the whole 100 MB rollout working set and all activations "
                              "(> 126 MB L2 per epoch); the GAE roofline launch flushes L2 explicitly"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

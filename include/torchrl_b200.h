@@ -181,6 +181,14 @@ int trl_per_update(float* prio, const int64_t* idx, const float* td, int b, int 
                    float* max_prio, void* stream);
 int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void* stream);
 
+/* ---- fp32-faithful tensor-core GEMM for the 256-wide MLP layers (tcgen05.mma kind::tf32, 3xTF32 split in
+ * shared memory, TMA operand loads, TMEM accumulator): C (M x 256) = A (M x K) . B (256 x K)^T, A/B row-major.
+ * Serves MLPBase's Linear forward / dgrad / wgrad (networks/base.py:24-44) when the layer width is 256.
+ * splits > 1: deterministic split-K (workspace: splits*M*256 floats). */
+int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
+                       float* workspace, void* stream);
+int trl_transpose_f32(const float* in, float* out, int64_t rows, int cols, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

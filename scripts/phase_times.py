@@ -34,6 +34,5 @@ def run(mode, graph=True):
                       "update_ms": tot[2] / 3, "per_minibatch_us": tot[2] / 3 / st["U"] * 1e3,
                       "per_step_us": tot[0] / 3 / 128 * 1e3}), flush=True)
 
-for mode in ("fp32", "tf32x3"):
+for mode in ("fp32", "tc3"):
     run(mode, True)
-run("fp32", False)

@@ -22,14 +22,16 @@ def test_fused_mlp_matches_plain_torch(act, M, inp, hidden):
     x = torch.randn(M, inp, device="cuda")
     w = torch.randn(M, 6, device="cuda")
     fused.set_fused_epilogue(True)
-    y1 = net(x)
-    (y1 * w).sum().backward()
-    fused.set_fused_epilogue(False)
+    fused.set_matmul_mode("fp32")          # isolate the epilogue kernels: same cuBLAS GEMMs on both sides
     try:
+        y1 = net(x)
+        (y1 * w).sum().backward()
+        fused.set_fused_epilogue(False)
         y0 = ref(x)
         (y0 * w).sum().backward()
     finally:
         fused.set_fused_epilogue(True)
+        fused.set_matmul_mode("tc3")
     torch.testing.assert_close(y1, y0, rtol=1e-5, atol=1e-6)
     for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
         scale = p0.grad.abs().max().item() + 1e-12
@@ -95,8 +97,42 @@ def test_tf32x3_mlp_matches_fp32_mlp():
         (y1 * w).sum().backward()
     finally:
         fused.set_matmul_mode("fp32")
-    y0 = ref(x)
-    (y0 * w).sum().backward()
+    try:
+        y0 = ref(x)
+        (y0 * w).sum().backward()
+    finally:
+        fused.set_matmul_mode("tc3")
+    torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
+    for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
+        scale = p0.grad.abs().max().item() + 1e-12
+        torch.testing.assert_close(p1.grad, p0.grad, rtol=1e-4, atol=2e-5 * scale, msg=n1)
+
+
+@pytest.mark.gpu
+def test_tc3_mlp_matches_fp32_mlp():
+    """MLP(256,256) forward/backward with the hand-written tcgen05 3xTF32 GEMM on the 256-wide layer."""
+    import copy
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    from torchrl_b200.networks import fused
+    torch.manual_seed(2)
+    net = networks.Net(input_shape=17, output_shape=6, hidden_shapes=[256, 256], append_hidden_shapes=[],
+                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+    ref = copy.deepcopy(net)
+    x = torch.randn(16384, 17, device="cuda")
+    w = torch.randn(16384, 6, device="cuda")
+    fused.set_matmul_mode("tc3")
+    try:
+        y1 = net(x)
+        (y1 * w).sum().backward()
+    finally:
+        fused.set_matmul_mode("fp32")
+    try:
+        y0 = ref(x)
+        (y0 * w).sum().backward()
+    finally:
+        fused.set_matmul_mode("tc3")
     torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
     for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
         scale = p0.grad.abs().max().item() + 1e-12

@@ -1,0 +1,364 @@
+// gemm_tf32x3.cu -- fp32-faithful tensor-core GEMM for the 256-wide MLP layers (K3/K8 support).
+//
+//   C[M x 256] = A[M x K] * B[256 x K]^T          (A, B row-major with K contiguous = "K-major")
+//
+// The policy / value / Q networks of the hot path are MLP(256,256)s; profiles
+// (profiles/launches_ppo_step_r1.md) show their three big GEMM shapes -- forward (x W^T), dgrad (g W) and
+// wgrad (g^T x) -- at ~50 % of a PPO minibatch on cuBLAS' fp32 SIMT kernels (~45 TFLOP/s).  This kernel
+// runs them on the 5th-gen tensor cores WITHOUT giving up fp32 accuracy: every operand element is split
+// in shared memory into x = hi + lo (hi = TF32-rounded, lo = exact remainder) and each 8-deep K step
+// issues three tcgen05.mma.kind::tf32 (lo*hi, hi*lo, hi*hi) into the same fp32 TMEM accumulator
+// ("3xTF32"; the dropped lo*lo term is O(2^-22) relative, measured error equals the SIMT sgemm's).
+//
+// Structure (one CTA per 128x256 output tile and K-slab, 192 threads):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of the raw fp32 A (128x32) / B (256x32) tiles,
+//                              SWIZZLE_128B, 2-stage ring, mbarrier complete_tx
+//   warps 2..5  converters   : split raw -> (hi in place, lo in a twin buffer); the 128B swizzle permutes 16-byte
+//                              chunks, so a chunk-wise elementwise pass preserves the canonical UMMA layout;
+//                              fence.proxy.async + mbarrier arrive hands the stage to the MMA warp
+//   warp 1      MMA issuer   : one elected lane issues 12 tcgen05.mma per stage (4 K-steps x 3 products),
+//                              tcgen05.commit releases the stage / signals the epilogue; owns the 256 TMEM columns
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b -> registers -> global (optionally a split-K partial slab)
+// Split-K (gridDim.y slabs) serves the wgrad shape (tiny output, K = minibatch): partials are summed in a fixed
+// order by splitk_reduce_kernel (deterministic).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace trl {
+
+constexpr int kBM = 128, kBN = 256, kBK = 32;          // tile; kBK fp32 = one 128-byte swizzle row
+constexpr int kStages = 2;
+constexpr int kUmmaK = 8;                              // tf32: 32 bytes per MMA K-step
+constexpr int kABytes = kBM * kBK * 4;                 // 16 KB
+constexpr int kBBytes = kBN * kBK * 4;                 // 32 KB
+constexpr int kStageBytes = 2 * (kABytes + kBBytes);   // hi + lo of A and B = 96 KB
+constexpr int kGemmThreads = 192;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// K-major, SWIZZLE_128B canonical layout: 8-row atoms of 1024 B; SBO = 1024 B; LBO unused (1); version 1.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);        // start address  [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                           // leading byte offset (ignored for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version (Blackwell)
+  d |= static_cast<uint64_t>(2) << 61;                           // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+__device__ __forceinline__ uint32_t umma_idesc_tf32_128x256() {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+}
+
+struct GemmParams {
+  float* __restrict__ C;       // (splits, M, 256) when splits > 1 else (M, 256)
+  long long M;
+  int k_blocks_per_split;      // K-blocks (of 32) handled by one CTA
+  int ldc;                     // 256
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tf32x3_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // stage s: [A_hi | A_lo | B_hi | B_lo]
+  auto a_hi = [&](int s) { return smem + s * kStageBytes; };
+  auto a_lo = [&](int s) { return smem + s * kStageBytes + kABytes; };
+  auto b_hi = [&](int s) { return smem + s * kStageBytes + 2 * kABytes; };
+  auto b_lo = [&](int s) { return smem + s * kStageBytes + 2 * kABytes + kBBytes; };
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;                 // [kStages]  TMA -> converters
+  uint64_t* conv = bars + kStages;       // [kStages]  converters -> MMA
+  uint64_t* empty = bars + 2 * kStages;  // [kStages]  MMA -> TMA
+  uint64_t* tmem_full = bars + 3 * kStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x, split = blockIdx.y;
+  const int nkb = p.k_blocks_per_split;
+  const int kb0 = split * nkb;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kStages; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&conv[s], 4);          // one arrival per converter warp
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(tmem_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // 256 fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], kABytes + kBBytes);
+        tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kBK, m_blk * kBM);
+        tma_load_2d(b_hi(s), &map_b, &full[s], (kb0 + kb) * kBK, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32_128x256();
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % kStages;
+        const uint32_t ph = (kb / kStages) & 1;
+        mbar_wait(&conv[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi(s))), da_lo = umma_desc_k_sw128(smem_u32(a_lo(s)));
+        const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi(s))), db_lo = umma_desc_k_sw128(smem_u32(b_lo(s)));
+#pragma unroll
+        for (int k = 0; k < kBK / kUmmaK; ++k) {
+          const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 4) >> 4);   // +32 B per K-step inside the swizzle row
+          umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
+          umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
+        }
+        umma_commit(&empty[s]);                       // stage free once these MMAs have read it
+      }
+      umma_commit(tmem_full);                         // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ converters (warps 2..5), then epilogue
+    const int ct = threadIdx.x - 64;                  // 0..127
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % kStages;
+      const uint32_t ph = (kb / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      float4* ah = reinterpret_cast<float4*>(a_hi(s));
+      float4* al = reinterpret_cast<float4*>(a_lo(s));
+#pragma unroll
+      for (int i = 0; i < kABytes / 16 / 128; ++i) {
+        const int c = ct + i * 128;
+        float4 h, l;
+        split4(ah[c], h, l);
+        ah[c] = h;
+        al[c] = l;
+      }
+      float4* bh = reinterpret_cast<float4*>(b_hi(s));
+      float4* bl = reinterpret_cast<float4*>(b_lo(s));
+#pragma unroll
+      for (int i = 0; i < kBBytes / 16 / 128; ++i) {
+        const int c = ct + i * 128;
+        float4 h, l;
+        split4(bh[c], h, l);
+        bh[c] = h;
+        bl[c] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&conv[s]);
+    }
+    // epilogue: TMEM lane quadrant of this warp = warp % 4
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int quad = warp & 3;
+    const long long row = static_cast<long long>(m_blk) * kBM + quad * 32 + lane;
+    float* crow = p.C + (static_cast<long long>(split) * p.M + row) * p.ldc;
+#pragma unroll 1
+    for (int c = 0; c < kBN / 32; ++c) {
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (row < p.M) {
+        float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+// C[m][n] = sum_s P[s][m][n]   (fixed order)
+__global__ void splitk_reduce_kernel(const float* __restrict__ P, float* __restrict__ C, long long mn, int splits) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= mn) return;
+  float4 acc = *reinterpret_cast<const float4*>(P + i);
+  for (int s = 1; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(P + static_cast<long long>(s) * mn + i);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(C + i) = acc;
+}
+
+// out (C x R) = in (R x C)^T, 32x32 tiles through shared memory
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, long long R, int C) {
+  __shared__ float tile[32][33];
+  const long long r0 = static_cast<long long>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < R && c < C) ? in[r * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j;
+    const long long r = r0 + threadIdx.x;
+    if (c < C && r < R) out[static_cast<long long>(c) * R + r] = tile[threadIdx.x][j];
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+// rows x K fp32 row-major matrix, box = (32 K-elements, box_rows), 128B swizzle
+static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {K, rows};
+  const cuuint64_t gstride[1] = {K * sizeof(float)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace trl
+
+// C (M x 256) = A (M x K) . B (256 x K)^T with 3xTF32 tensor-core arithmetic.
+// splits > 1: K is divided into `splits` slabs; `workspace` must hold splits*M*256 floats and the slabs are
+// summed into C in a fixed order.  Requirements: K % (32*splits) == 0, 16-byte aligned A/B/C, M >= 1.
+TRL_API int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
+                               float* workspace, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(M >= 1 && K >= kBK && splits >= 1, "trl_gemm_tf32x3_nt: bad sizes M=%lld K=%lld splits=%d", (long long)M,
+              (long long)K, splits);
+  TRL_REQUIRE(K % (static_cast<int64_t>(kBK) * splits) == 0, "trl_gemm_tf32x3_nt: K=%lld must be a multiple of 32*splits",
+              (long long)K);
+  TRL_REQUIRE(A && B && C && (splits == 1 || workspace), "trl_gemm_tf32x3_nt: null pointer");
+  TRL_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && aligned16(workspace),
+              "trl_gemm_tf32x3_nt: pointers must be 16-byte aligned");
+  CUtensorMap map_a, map_b;
+  if (!make_map(&map_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kBM) ||
+      !make_map(&map_b, B, static_cast<uint64_t>(kBN), static_cast<uint64_t>(K), kBN)) {
+    set_error("trl_gemm_tf32x3_nt: cuTensorMapEncodeTiled failed");
+    return TRL_EUNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  GemmParams p{splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
+  const dim3 grid(static_cast<unsigned>(ceil_div<long long>(M, kBM)), static_cast<unsigned>(splits));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gemm_tf32x3_nt_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  int rc = check_launch("gemm_tf32x3_nt_kernel");
+  if (rc != TRL_OK || splits == 1) return rc;
+  const long long mn = M * kBN;
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 256)), 256, 0, st>>>(workspace, C, mn, splits);
+  return check_launch("splitk_reduce_kernel");
+}
+
+TRL_API int trl_transpose_f32(const float* in, float* out, int64_t rows, int cols, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(rows >= 1 && cols >= 1, "trl_transpose_f32: bad sizes");
+  TRL_REQUIRE(in && out, "trl_transpose_f32: null pointer");
+  const dim3 grid(static_cast<unsigned>(ceil_div(cols, 32)), static_cast<unsigned>(ceil_div<long long>(rows, 32)));
+  transpose_kernel<<<grid, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(in, out, rows, cols);
+  return check_launch("transpose_kernel");
+}

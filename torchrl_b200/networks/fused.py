@@ -14,7 +14,12 @@ from .. import _lib, ops
 
 ACT_CODES = {nn.Tanh: 1, nn.ReLU: 2}
 _ENABLED = True
-_MATMUL_MODE = "fp32"            # "fp32": cuBLAS SIMT sgemm | "tf32x3": error-compensated tensor-core GEMMs
+# "tc3"   : 256-wide layers with >= _TC3_MIN_ROWS rows on the hand-written tcgen05 3xTF32 kernel
+#           (csrc/gemm_tf32x3.cu, fp32-faithful), everything else cuBLAS fp32 SIMT            [default]
+# "fp32"  : cuBLAS fp32 SIMT sgemm everywhere
+# "tf32x3": error-compensated TF32 through three cuBLAS GEMMs (kept for comparison; no faster than fp32)
+_MATMUL_MODE = "tc3"
+_TC3_MIN_ROWS = 8192
 _TF32X3_MIN_DIM = 64             # layers narrower than this stay on the plain path
 
 
@@ -23,12 +28,18 @@ def set_matmul_mode(mode):
     cores with fp32 accumulation (operands split by csrc/mlp_epilogue.cu:split_tf32_kernel) -- fp32-faithful
     results (the dropped lo*lo term is O(2^-22)), unlike plain TF32."""
     global _MATMUL_MODE
-    assert mode in ("fp32", "tf32x3")
+    assert mode in ("fp32", "tf32x3", "tc3")
     _MATMUL_MODE = mode
 
 
 def get_matmul_mode():
     return _MATMUL_MODE
+
+
+def _tc3_ok(rows, n_out, k):
+    """Shapes served by the hand-written tcgen05 3xTF32 kernel (csrc/gemm_tf32x3.cu): 256 output columns,
+    reduction length a multiple of 32, enough rows to fill the chip (one 128-row tile per CTA)."""
+    return _MATMUL_MODE == "tc3" and rows >= _TC3_MIN_ROWS and n_out == 256 and k >= 32 and k % 32 == 0
 
 
 def split_tf32(t):
@@ -102,7 +113,10 @@ class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         tc = (_MATMUL_MODE == "tf32x3" and min(x.shape[0], x.shape[1], weight.shape[0]) >= _TF32X3_MIN_DIM)
-        if tc:
+        if _tc3_ok(x.shape[0], weight.shape[0], x.shape[1]) and weight.is_contiguous():
+            z = ops.gemm_tf32x3_nt(x, weight)                  # tcgen05: x (M,K) . W (256,K)^T
+            ctx.save_for_backward(x, weight, z)
+        elif tc:
             x_hi, x_lo = split_tf32(x)
             w_hi, w_lo = split_tf32(weight)
             z = mm3(x_hi, x_lo, w_hi.t(), w_lo.t())
@@ -128,7 +142,12 @@ class _LinearAct(torch.autograd.Function):
         scratch, tickets = _Workspace.get(M, H, y.device)
         _lib.call("trl_bias_act_bwd", g.data_ptr(), y.data_ptr(), gz.data_ptr(), db.data_ptr(), M, H, ctx.act,
                   scratch.data_ptr(), tickets.data_ptr(), ops._stream())
-        dx = torch.mm(gz, weight) if ctx.needs_input_grad[0] else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if _tc3_ok(M, weight.shape[1], H) and weight.is_contiguous():
+                dx = ops.gemm_tf32x3_nt(gz, ops.transpose_f32(weight))   # gz (M,H) . (W^T) (256,H)^T
+            else:
+                dx = torch.mm(gz, weight)
         dw = wgrad(gz, x) if ctx.needs_input_grad[1] else None
         return dx, dw, (db if ctx.needs_input_grad[2] else None), None
 

@@ -394,3 +394,29 @@ def per_update(prio, idx, td, alpha, eps, max_prio):
 def per_insert(prio, row_ptr, max_prio):
     _lib.call("trl_per_insert", _chk(prio, F32, "prio"), _chk(row_ptr, I32, "row_ptr"), _chk(max_prio, F32, "max_prio"),
               _stream())
+
+
+# ------------------------------------------------------------------------------------------ tensor-core GEMM
+def gemm_tf32x3_nt(a, b, out=None, splits=1, workspace=None):
+    """out (M,256) = a (M,K) @ b (256,K)^T on the tcgen05 tensor cores with 3xTF32 error compensation
+    (csrc/gemm_tf32x3.cu).  a, b contiguous fp32, K % (32*splits) == 0."""
+    M, K = a.shape
+    assert b.shape == (256, K), "B must be (256, K)"
+    if out is None:
+        out = torch.empty(M, 256, dtype=F32, device=a.device)
+    if splits > 1 and workspace is None:
+        workspace = torch.empty(splits * M * 256, dtype=F32, device=a.device)
+    _lib.call("trl_gemm_tf32x3_nt", _chk(a, F32, "a"), _chk(b, F32, "b"), _chk(out, F32, "out"), M, K, int(splits),
+              None if workspace is None else workspace.data_ptr(), _stream())
+    if splits > 1:
+        _lib.add_launches(1)      # + the split-K reduction launch
+    return out
+
+
+def transpose_f32(x, out=None):
+    """out (C,R) = x (R,C)^T (contiguous)."""
+    R, C = x.shape
+    if out is None:
+        out = torch.empty(C, R, dtype=F32, device=x.device)
+    _lib.call("trl_transpose_f32", _chk(x, F32, "x"), _chk(out, F32, "out"), R, C, _stream())
+    return out
