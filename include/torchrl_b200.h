@@ -187,6 +187,9 @@ int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void*
  * splits > 1: deterministic split-K (workspace: splits*M*256 floats). */
 int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
                        float* workspace, void* stream);
+/* C (M x 256) = A (K x M)^T . B (K x 256): the weight-gradient shape (operands M/N-major, no transposes). */
+int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
+                       float* workspace, void* stream);
 int trl_transpose_f32(const float* in, float* out, int64_t rows, int cols, void* stream);
 
 #ifdef __cplusplus

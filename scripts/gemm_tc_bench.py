@@ -19,3 +19,7 @@ for sp in (32, 64, 128):
     print("wgrad 256x16384x256 splits=%d: tcgen05 %.1f us" % (sp, bench(lambda: ops.gemm_tf32x3_nt(at, bt, o2, splits=sp, workspace=ws))))
 g = torch.randn(16384, 256, device="cuda")
 print("transpose 16384x256: %.1f us" % bench(lambda: ops.transpose_f32(g)))
+gz = torch.randn(16384, 256, device="cuda"); xx = torch.randn(16384, 256, device="cuda")
+for sp in (32, 64, 128):
+    ws = torch.empty(sp * 256 * 256, device="cuda")
+    print("wgrad tn (no transposes) splits=%d: tcgen05 %.1f us" % (sp, bench(lambda: ops.gemm_tf32x3_tn(gz, xx, o2, splits=sp, workspace=ws))))

@@ -61,6 +61,7 @@ SIGNATURES = {
     "trl_per_update": [vp, vp, vp, i32, i32, f32, f32, vp, vp],
     "trl_per_insert": [vp, vp, vp, vp],
     "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp],
+    "trl_gemm_tf32x3_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_transpose_f32": [vp, vp, i64, i32, vp],
     "trl_offpolicy_scratch_doubles": [i64],
     "trl_td_target": [vp, vp, vp, vp, vp, vp, f32, f32, i64, vp, vp, vp, vp, vp],

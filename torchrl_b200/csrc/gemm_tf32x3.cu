@@ -19,6 +19,9 @@
 //   warp 1      MMA issuer   : one elected lane issues 12 tcgen05.mma per stage (4 K-steps x 3 products),
 //                              tcgen05.commit releases the stage / signals the epilogue; owns the 256 TMEM columns
 //   warps 2..5  epilogue     : tcgen05.ld 32x32b -> registers -> global (optionally a split-K partial slab)
+// Accuracy: the tensor core's fp32 accumulation truncates, so the error grows ~linearly with the reduction length
+// accumulated in TMEM: 2e-6 (relative to max|C|) at 256, 7e-6 at 1024 -- vs 7e-7 for the SIMT sgemm and 3e-4 for
+// plain TF32.  Callers keep K/splits <= 256 (the MLP layers here: K = 256; wgrad: 16384/64).
 // Split-K (gridDim.y slabs) serves the wgrad shape (tiny output, K = minibatch): partials are summed in a fixed
 // order by splitk_reduce_kernel (deterministic).
 #include "common.cuh"
@@ -77,9 +80,26 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                           // layout type: SWIZZLE_128B
   return d;
 }
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
+// MN-major fp32 operands: the ONLY shared-memory layout tcgen05 accepts for M/N-major tf32 is
+// SWIZZLE_128B_BASE32B (layout type 1; cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the
+// only available smem layout"): rows of 128 B = 32 contiguous M/N elements at one reduction index, atoms of
+// 4 such rows (512 B) in which the 32-byte unit index is XORed with the row index (Swizzle<2,5,2> on byte
+// addresses) -- exactly what TMA's CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes.  SBO = 512 B between successive
+// 4-row atoms along K, LBO = byte distance between successive groups of 32 M/N elements.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_32b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(1) << 61;                           // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+// kind::tf32, fp32 accumulate, M = 128, N = 256; MN = both operands M/N-major instead of K-major
+template <bool MN>
 __device__ __forceinline__ uint32_t umma_idesc_tf32_128x256() {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+  return (1u << 4) | (2u << 7) | (2u << 10) | (MN ? (1u << 15) | (1u << 16) : 0u) |
+         (static_cast<uint32_t>(kBN >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -109,9 +129,12 @@ struct GemmParams {
   int ldc;                     // 256
 };
 
+// MN == false: C = A . B^T with A (M x K), B (256 x K) row-major (K-major operands).
+// MN == true : C = A^T . B  with A (K x M), B (K x 256) row-major (M/N-major operands; the wgrad shape).
+template <bool MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tf32x3_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      const GemmParams p) {
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   // stage s: [A_hi | A_lo | B_hi | B_lo]
@@ -163,24 +186,37 @@ gemm_tf32x3_nt_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], kABytes + kBBytes);
-        tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kBK, m_blk * kBM);
-        tma_load_2d(b_hi(s), &map_b, &full[s], (kb0 + kb) * kBK, 0);
+        if (!MN) {
+          tma_load_2d(a_hi(s), &map_a, &full[s], (kb0 + kb) * kBK, m_blk * kBM);
+          tma_load_2d(b_hi(s), &map_b, &full[s], (kb0 + kb) * kBK, 0);
+        } else {
+          // one (32 M/N elements x 32 reduction rows) box per group of 32 output rows / columns, 4 KB apart
+#pragma unroll
+          for (int g = 0; g < kBM / 32; ++g)
+            tma_load_2d(a_hi(s) + g * 4096, &map_a, &full[s], m_blk * kBM + g * 32, (kb0 + kb) * kBK);
+#pragma unroll
+          for (int g = 0; g < kBN / 32; ++g)
+            tma_load_2d(b_hi(s) + g * 4096, &map_b, &full[s], g * 32, (kb0 + kb) * kBK);
+        }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32_128x256();
+      const uint32_t idesc = umma_idesc_tf32_128x256<MN>();
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&conv[s], ph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t da_hi = umma_desc_k_sw128(smem_u32(a_hi(s))), da_lo = umma_desc_k_sw128(smem_u32(a_lo(s)));
-        const uint64_t db_hi = umma_desc_k_sw128(smem_u32(b_hi(s))), db_lo = umma_desc_k_sw128(smem_u32(b_lo(s)));
+        const uint64_t da_hi = MN ? umma_desc_mn_sw128_32b(smem_u32(a_hi(s)), 4096) : umma_desc_k_sw128(smem_u32(a_hi(s)));
+        const uint64_t da_lo = MN ? umma_desc_mn_sw128_32b(smem_u32(a_lo(s)), 4096) : umma_desc_k_sw128(smem_u32(a_lo(s)));
+        const uint64_t db_hi = MN ? umma_desc_mn_sw128_32b(smem_u32(b_hi(s)), 4096) : umma_desc_k_sw128(smem_u32(b_hi(s)));
+        const uint64_t db_lo = MN ? umma_desc_mn_sw128_32b(smem_u32(b_lo(s)), 4096) : umma_desc_k_sw128(smem_u32(b_lo(s)));
 #pragma unroll
         for (int k = 0; k < kBK / kUmmaK; ++k) {
-          const uint64_t adv = static_cast<uint64_t>((k * kUmmaK * 4) >> 4);   // +32 B per K-step inside the swizzle row
+          // K-major: +32 B per K-step inside the 128 B swizzle row; MN-major: +1024 B = 8 reduction rows further
+          const uint64_t adv = static_cast<uint64_t>((MN ? k * 1024 : k * kUmmaK * 4) >> 4);
           umma_tf32(tmem_base, da_lo + adv, db_hi + adv, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_tf32(tmem_base, da_hi + adv, db_lo + adv, idesc, 1u);
           umma_tf32(tmem_base, da_hi + adv, db_hi + adv, idesc, 1u);
@@ -303,8 +339,9 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// rows x K fp32 row-major matrix, box = (32 K-elements, box_rows), 128B swizzle
-static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+// rows x K fp32 row-major matrix, box = (32 contiguous elements, box_rows), 128B swizzle
+static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return false;
   const cuuint64_t gdim[2] = {K, rows};
@@ -312,7 +349,7 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_
   const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_rows};
   const cuuint32_t estr[2] = {1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
-             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -339,15 +376,51 @@ TRL_API int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   GemmParams p{splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
   const dim3 grid(static_cast<unsigned>(ceil_div<long long>(M, kBM)), static_cast<unsigned>(splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gemm_tf32x3_nt_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
-  int rc = check_launch("gemm_tf32x3_nt_kernel");
+  gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  int rc = check_launch("gemm_tf32x3_kernel<nt>");
+  if (rc != TRL_OK || splits == 1) return rc;
+  const long long mn = M * kBN;
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 256)), 256, 0, st>>>(workspace, C, mn, splits);
+  return check_launch("splitk_reduce_kernel");
+}
+
+// C (M x 256) = A (K x M)^T . B (K x 256): both operands with the reduction index as the ROW index (the
+// weight-gradient shape dW = g^T x).  M % 128 == 0, K % (32*splits) == 0, split-K as above.
+TRL_API int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
+                               float* workspace, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(M >= kBM && M % kBM == 0 && K >= kBK && splits >= 1, "trl_gemm_tf32x3_tn: bad sizes M=%lld K=%lld splits=%d",
+              (long long)M, (long long)K, splits);
+  TRL_REQUIRE(K % (static_cast<int64_t>(kBK) * splits) == 0, "trl_gemm_tf32x3_tn: K=%lld must be a multiple of 32*splits",
+              (long long)K);
+  TRL_REQUIRE(A && B && C && (splits == 1 || workspace), "trl_gemm_tf32x3_tn: null pointer");
+  TRL_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && aligned16(workspace),
+              "trl_gemm_tf32x3_tn: pointers must be 16-byte aligned");
+  CUtensorMap map_a, map_b;
+  // (K rows) x (M | 256 contiguous) matrices, boxes of 32 contiguous elements x 32 reduction rows
+  if (!make_map(&map_a, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) ||
+      !make_map(&map_b, B, static_cast<uint64_t>(K), static_cast<uint64_t>(kBN), 32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) {
+    set_error("trl_gemm_tf32x3_tn: cuTensorMapEncodeTiled failed");
+    return TRL_EUNSUPPORTED;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+    attr_set = true;
+  }
+  GemmParams p{splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
+  const dim3 grid(static_cast<unsigned>(M / kBM), static_cast<unsigned>(splits));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  int rc = check_launch("gemm_tf32x3_kernel<tn>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
   splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 256)), 256, 0, st>>>(workspace, C, mn, splits);

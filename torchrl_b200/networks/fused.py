@@ -50,6 +50,9 @@ def split_tf32(t):
     return hi, lo
 
 
+_WGRAD_WS = {}
+
+
 def wgrad(gz, x):
     """dW = gz^T @ x  for gz (M,H), x (M,K): split-K batched GEMM + partial sum.
 
@@ -59,6 +62,13 @@ def wgrad(gz, x):
     CTAs; the S partial products are summed in a fixed order (deterministic)."""
     M, H = gz.shape
     K = x.shape[1]
+    if _tc3_ok(M, K, M) and H % 128 == 0 and M % (32 * 64) == 0:
+        # tcgen05 3xTF32, operands consumed M/N-major from their row-major storage, deterministic split-K
+        key = (H, str(gz.device))
+        ws = _WGRAD_WS.get(key)
+        if ws is None:
+            ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
+        return ops.gemm_tf32x3_tn(gz, x, splits=64, workspace=ws)
     if H < 4 or M < 4096:
         return torch.mm(gz.t(), x)
     S = 16 if min(H, K) >= 128 else 64

@@ -413,6 +413,22 @@ def gemm_tf32x3_nt(a, b, out=None, splits=1, workspace=None):
     return out
 
 
+def gemm_tf32x3_tn(a, b, out=None, splits=1, workspace=None):
+    """out (M,256) = a (K,M)^T @ b (K,256): the weight-gradient shape dW = g^T x on the tcgen05 tensor cores
+    (3xTF32), operands consumed M/N-major straight from their row-major storage (no transposes)."""
+    K, M = a.shape
+    assert b.shape == (K, 256), "B must be (K, 256)"
+    if out is None:
+        out = torch.empty(M, 256, dtype=F32, device=a.device)
+    if splits > 1 and workspace is None:
+        workspace = torch.empty(splits * M * 256, dtype=F32, device=a.device)
+    _lib.call("trl_gemm_tf32x3_tn", _chk(a, F32, "a"), _chk(b, F32, "b"), _chk(out, F32, "out"), M, K, int(splits),
+              None if workspace is None else workspace.data_ptr(), _stream())
+    if splits > 1:
+        _lib.add_launches(1)
+    return out
+
+
 def transpose_f32(x, out=None):
     """out (C,R) = x (R,C)^T (contiguous)."""
     R, C = x.shape
