@@ -24,6 +24,7 @@ import torch
 
 from ... import ops
 from ...flat import FlatParams
+from ...networks import fused
 from .. import utils as atu
 from .a2c import A2C
 
@@ -101,7 +102,13 @@ class PPO(A2C):
         return st
 
     def _mb_body(self):
-        """One minibatch update reading its row indices at device position `pos`."""
+        """One minibatch update reading its row indices at device position `upd`.  Layer gradients go
+        straight into the flat gradient buffer (networks.fused.direct_grad): every parameter gets exactly
+        one contribution per minibatch and the fused Adam step left the buffer zeroed."""
+        with fused.direct_grad():
+            self._mb_body_inner()
+
+    def _mb_body_inner(self):
         st, rb = self._mb_state, self.replay_buffer
         batch = rb.gather_rows(st["perm"], st["keys"], pos_ptr=st["upd"], rows=st["b"])
         info = st["info"][0]

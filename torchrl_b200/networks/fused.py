@@ -53,7 +53,7 @@ def split_tf32(t):
 _WGRAD_WS = {}
 
 
-def wgrad(gz, x):
+def wgrad(gz, x, out=None):
     """dW = gz^T @ x  for gz (M,H), x (M,K): split-K batched GEMM + partial sum.
 
     The direct `mm(gz.t(), x)` lands on a slow cuBLAS `nt` kernel for this shape class (tiny output, K =
@@ -68,16 +68,17 @@ def wgrad(gz, x):
         ws = _WGRAD_WS.get(key)
         if ws is None:
             ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
-        return ops.gemm_tf32x3_tn(gz, x, splits=64, workspace=ws)
+        return ops.gemm_tf32x3_tn(gz, x, out=out, splits=64, workspace=ws)
     if H < 4 or M < 4096:
-        return torch.mm(gz.t(), x)
+        return torch.mm(gz.t(), x, out=out) if out is not None else torch.mm(gz.t(), x)
     S = 16 if min(H, K) >= 128 else 64
     while S > 1 and M % S:
         S //= 2
     if S == 1:
-        return torch.mm(gz.t(), x)
+        return torch.mm(gz.t(), x, out=out) if out is not None else torch.mm(gz.t(), x)
     m = M // S
-    return torch.bmm(gz.view(S, m, H).transpose(1, 2), x.view(S, m, K)).sum(0)
+    part = torch.bmm(gz.view(S, m, H).transpose(1, 2), x.view(S, m, K))
+    return torch.sum(part, 0, out=out) if out is not None else part.sum(0)
 
 
 def mm3(a_hi, a_lo, b_hi, b_lo):
@@ -91,6 +92,31 @@ def mm3(a_hi, a_lo, b_hi, b_lo):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     return out
+
+
+_DIRECT_GRAD = False
+
+
+class direct_grad:
+    """Context manager: inside it the fused layers write weight / bias gradients STRAIGHT into the parameters'
+    pre-allocated `.grad` storage (views of the agent's flat gradient buffer, zeroed by the fused Adam step) and
+    return None to autograd, which removes one AccumulateGrad add-kernel per parameter tensor.  Valid only
+    when every parameter receives exactly one gradient contribution per backward and `.grad` is zero on
+    entry -- true for the PPO minibatch update, which is the only user."""
+
+    def __enter__(self):
+        global _DIRECT_GRAD
+        self.prev = _DIRECT_GRAD
+        _DIRECT_GRAD = True
+
+    def __exit__(self, *a):
+        global _DIRECT_GRAD
+        _DIRECT_GRAD = self.prev
+
+
+def _grad_out(param):
+    """The parameter's own `.grad` storage when direct mode is on (else None)."""
+    return param.grad if (_DIRECT_GRAD and param.grad is not None) else None
 
 
 def set_fused_epilogue(flag):
@@ -138,6 +164,7 @@ class _LinearAct(torch.autograd.Function):
                   act, ops._stream())
         ctx.act = act
         ctx.tc = tc
+        ctx.params = (weight, bias)        # the Parameter objects themselves (for direct-grad mode)
         return z
 
     @staticmethod
@@ -148,7 +175,9 @@ class _LinearAct(torch.autograd.Function):
         g = g if g.is_contiguous() else g.contiguous()
         M, H = y.shape
         gz = torch.empty_like(y)
-        db = torch.empty(H, dtype=torch.float32, device=y.device)
+        w_param, b_param = ctx.params
+        db_out, dw_out = _grad_out(b_param), _grad_out(w_param)
+        db = db_out if db_out is not None else torch.empty(H, dtype=torch.float32, device=y.device)
         scratch, tickets = _Workspace.get(M, H, y.device)
         _lib.call("trl_bias_act_bwd", g.data_ptr(), y.data_ptr(), gz.data_ptr(), db.data_ptr(), M, H, ctx.act,
                   scratch.data_ptr(), tickets.data_ptr(), ops._stream())
@@ -158,8 +187,9 @@ class _LinearAct(torch.autograd.Function):
                 dx = ops.gemm_tf32x3_nt(gz, ops.transpose_f32(weight))   # gz (M,H) . (W^T) (256,H)^T
             else:
                 dx = torch.mm(gz, weight)
-        dw = wgrad(gz, x) if ctx.needs_input_grad[1] else None
-        return dx, dw, (db if ctx.needs_input_grad[2] else None), None
+        dw = wgrad(gz, x, out=dw_out) if ctx.needs_input_grad[1] else None
+        return (dx, None if dw_out is not None else dw,
+                None if db_out is not None else (db if ctx.needs_input_grad[2] else None), None)
 
 
 def _backward_tc(ctx, g):
@@ -186,16 +216,21 @@ class _LinearPlain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.params = (weight, bias)
         return torch.addmm(bias, x, weight.t())
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         g = g if g.is_contiguous() else g.contiguous()
+        w_param, b_param = ctx.params
+        db_out, dw_out = _grad_out(b_param), _grad_out(w_param)
         dx = torch.mm(g, weight) if ctx.needs_input_grad[0] else None
-        dw = wgrad(g, x) if ctx.needs_input_grad[1] else None
-        db = g.sum(0) if ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        dw = wgrad(g, x, out=dw_out) if ctx.needs_input_grad[1] else None
+        db = None
+        if ctx.needs_input_grad[2]:
+            db = torch.sum(g, 0, out=db_out) if db_out is not None else g.sum(0)
+        return dx, None if dw_out is not None else dw, None if db_out is not None else db
 
 
 def linear_plain(x, fc):
