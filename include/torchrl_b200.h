@@ -184,13 +184,25 @@ int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void*
 /* ---- fp32-faithful tensor-core GEMM for the 256-wide MLP layers (tcgen05.mma kind::tf32, 3xTF32 split in
  * shared memory, TMA operand loads, TMEM accumulator): C (M x 256) = A (M x K) . B (256 x K)^T, A/B row-major.
  * Serves MLPBase's Linear forward / dgrad / wgrad (networks/base.py:24-44) when the layer width is 256.
- * splits > 1: deterministic split-K (workspace: splits*M*256 floats). */
+ * splits > 1: deterministic split-K (workspace: splits*M*256 floats).  bias != NULL (splits == 1): the Linear
+ * epilogue C = act(A B^T + bias) is fused (act: 0 none, 1 tanh, 2 relu). */
 int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
-                       float* workspace, void* stream);
+                       float* workspace, const float* bias, int act, void* stream);
 /* C (M x 256) = A (K x M)^T . B (K x 256): the weight-gradient shape (operands M/N-major, no transposes). */
 int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
                        float* workspace, void* stream);
 int trl_transpose_f32(const float* in, float* out, int64_t rows, int cols, void* stream);
+
+/* ---- "skinny" Linear layers of the small MLPs (first layer K = obs_dim, output layer N = act_dim / 1;
+ * networks/base.py:24-44, networks/nets.py:13-52): memory-bound fp32 kernels, bias / activation fused. */
+int trl_skinny_k_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t M, int K, int H,
+                     int act, void* stream);                         /* Y = act(X W^T + b), K <= 128 */
+int64_t trl_skinny_tn_scratch_floats(int64_t M, int H, int K);
+int trl_skinny_tn(const float* A, const float* B, float* Out, float* colsum, int64_t M, int H, int K,
+                  int out_transposed, float* scratch, void* stream);  /* Out = A^T B (K <= 32) [+ colsum(B)] */
+int trl_skinny_n_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t M, int H, int N,
+                     void* stream);                                   /* Y = X W^T + b, N <= 8 */
+int trl_skinny_n_dgrad(const float* G, const float* W, float* dX, int64_t M, int H, int N, void* stream);
 
 #ifdef __cplusplus
 }

@@ -137,3 +137,38 @@ def test_tc3_mlp_matches_fp32_mlp():
     for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
         scale = p0.grad.abs().max().item() + 1e-12
         torch.testing.assert_close(p1.grad, p0.grad, rtol=1e-4, atol=2e-5 * scale, msg=n1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("inp,out,M", [(17, 6, 16384), (17, 1, 16384), (23, 1, 4096), (17, 8, 1500)])
+def test_skinny_layers_match_plain_torch(inp, out, M):
+    """First layer (K = obs_dim) and output layer (N = act_dim / 1) through csrc/skinny.cu vs cuBLAS."""
+    import copy
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    from torchrl_b200.networks import fused
+    torch.manual_seed(inp * out)
+    net = networks.Net(input_shape=inp, output_shape=out, hidden_shapes=[256, 256], append_hidden_shapes=[],
+                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+    ref = copy.deepcopy(net)
+    x = torch.randn(M, inp, device="cuda", requires_grad=True)
+    x0 = x.detach().clone().requires_grad_()
+    w = torch.randn(M, out, device="cuda")
+    fused.set_skinny(True)
+    try:
+        y1 = net(x)
+        (y1 * w).sum().backward()
+    finally:
+        fused.set_skinny(False)
+    fused.set_matmul_mode("fp32")
+    try:
+        y0 = ref(x0)
+        (y0 * w).sum().backward()
+    finally:
+        fused.set_matmul_mode("tc3")
+    torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
+    torch.testing.assert_close(x.grad, x0.grad, rtol=1e-4, atol=1e-5 * x0.grad.abs().max().item())
+    for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
+        scale = p0.grad.abs().max().item() + 1e-12
+        torch.testing.assert_close(p1.grad, p0.grad, rtol=1e-4, atol=2e-5 * scale, msg=n1)

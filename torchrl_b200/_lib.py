@@ -60,9 +60,14 @@ SIGNATURES = {
     "trl_per_sample": [vp, i32, vp, i32, f32, vp, vp, vp],
     "trl_per_update": [vp, vp, vp, i32, i32, f32, f32, vp, vp],
     "trl_per_insert": [vp, vp, vp, vp],
-    "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp],
+    "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp, i32, vp],
     "trl_gemm_tf32x3_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_transpose_f32": [vp, vp, i64, i32, vp],
+    "trl_skinny_k_fwd": [vp, vp, vp, vp, i64, i32, i32, i32, vp],
+    "trl_skinny_tn_scratch_floats": [i64, i32, i32],
+    "trl_skinny_tn": [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
+    "trl_skinny_n_fwd": [vp, vp, vp, vp, i64, i32, i32, vp],
+    "trl_skinny_n_dgrad": [vp, vp, vp, i64, i32, i32, vp],
     "trl_offpolicy_scratch_doubles": [i64],
     "trl_td_target": [vp, vp, vp, vp, vp, vp, f32, f32, i64, vp, vp, vp, vp, vp],
     "trl_td3_smooth_action": [vp, vp, f32, f32, u64, vp, i64, vp, vp],
@@ -72,7 +77,8 @@ SIGNATURES = {
     "trl_qr_dqn_loss": [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, vp],
 }
 _RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles": ctypes.c_int64,
-             "trl_offpolicy_scratch_doubles": ctypes.c_int64, "trl_bias_act_bwd_scratch_floats": ctypes.c_int64}
+             "trl_offpolicy_scratch_doubles": ctypes.c_int64, "trl_bias_act_bwd_scratch_floats": ctypes.c_int64,
+             "trl_skinny_tn_scratch_floats": ctypes.c_int64}
 # entry points that return a value rather than an error code
 _VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas",
                 "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")

@@ -123,6 +123,8 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
 }
 
 struct GemmParams {
+  const float* __restrict__ bias;  // (256) added in the epilogue, or nullptr
+  int act;                         // 0 none, 1 tanh, 2 relu (applied after the bias)
   float* __restrict__ C;       // (splits, M, 256) when splits > 1 else (M, 256)
   long long M;
   int k_blocks_per_split;      // K-blocks (of 32) handled by one CTA
@@ -279,9 +281,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (row < p.M) {
         float4* dst = reinterpret_cast<float4*>(crow + c * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+        for (int j = 0; j < 8; ++j) {
+          float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                 __uint_as_float(r[4 * j + 3]));
+          if (p.bias) {   // fused Linear epilogue: z + b, then the activation (same op order as bias_act_fwd_kernel)
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * j);
+            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            if (p.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            else if (p.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          }
+          dst[j] = v;
+        }
       }
     }
   }
@@ -293,16 +303,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-// C[m][n] = sum_s P[s][m][n]   (fixed order)
-__global__ void splitk_reduce_kernel(const float* __restrict__ P, float* __restrict__ C, long long mn, int splits) {
-  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
-  if (i >= mn) return;
-  float4 acc = *reinterpret_cast<const float4*>(P + i);
-  for (int s = 1; s < splits; ++s) {
-    const float4 v = *reinterpret_cast<const float4*>(P + static_cast<long long>(s) * mn + i);
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+// C[m][n] = sum_s P[s][m][n]   (fixed order: 4 interleaved partial sums per element combined pairwise)
+// CTA = 64 float4 outputs x 4 split groups; group g sums splits g, g+4, ...; groups combined through smem.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ P, float* __restrict__ C,
+                                                           long long mn, int splits) {
+  __shared__ float4 sh[4][64];
+  const int o = threadIdx.x & 63, g = threadIdx.x >> 6;
+  const long long i = (static_cast<long long>(blockIdx.x) * 64 + o) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < mn) {
+#pragma unroll 4
+    for (int s = g; s < splits; s += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(P + static_cast<long long>(s) * mn + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  *reinterpret_cast<float4*>(C + i) = acc;
+  sh[g][o] = acc;
+  __syncthreads();
+  if (g == 0 && i < mn) {
+    const float4 a = sh[0][o], b = sh[1][o], c = sh[2][o], d = sh[3][o];
+    *reinterpret_cast<float4*>(C + i) =
+        make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+  }
 }
 
 // out (C x R) = in (R x C)^T, 32x32 tiles through shared memory
@@ -355,19 +377,21 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_
 
 }  // namespace trl
 
-// C (M x 256) = A (M x K) . B (256 x K)^T with 3xTF32 tensor-core arithmetic.
+// C (M x 256) = act(A (M x K) . B (256 x K)^T [+ bias]) with 3xTF32 tensor-core arithmetic (bias NULL: plain GEMM).
 // splits > 1: K is divided into `splits` slabs; `workspace` must hold splits*M*256 floats and the slabs are
 // summed into C in a fixed order.  Requirements: K % (32*splits) == 0, 16-byte aligned A/B/C, M >= 1.
 TRL_API int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
-                               float* workspace, void* stream) {
+                               float* workspace, const float* bias, int act, void* stream) {
   using namespace trl;
   TRL_REQUIRE(M >= 1 && K >= kBK && splits >= 1, "trl_gemm_tf32x3_nt: bad sizes M=%lld K=%lld splits=%d", (long long)M,
               (long long)K, splits);
   TRL_REQUIRE(K % (static_cast<int64_t>(kBK) * splits) == 0, "trl_gemm_tf32x3_nt: K=%lld must be a multiple of 32*splits",
               (long long)K);
   TRL_REQUIRE(A && B && C && (splits == 1 || workspace), "trl_gemm_tf32x3_nt: null pointer");
-  TRL_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && aligned16(workspace),
+  TRL_REQUIRE(aligned16(A) && aligned16(B) && aligned16(C) && aligned16(workspace) && aligned16(bias),
               "trl_gemm_tf32x3_nt: pointers must be 16-byte aligned");
+  TRL_REQUIRE(!(bias && splits > 1), "trl_gemm_tf32x3_nt: the bias/activation epilogue needs splits == 1");
+  TRL_REQUIRE(act >= 0 && act <= 2, "trl_gemm_tf32x3_nt: unknown activation %d", act);
   CUtensorMap map_a, map_b;
   if (!make_map(&map_a, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), kBM) ||
       !make_map(&map_b, B, static_cast<uint64_t>(kBN), static_cast<uint64_t>(K), kBN)) {
@@ -380,14 +404,14 @@ TRL_API int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  GemmParams p{splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
+  GemmParams p{bias, act, splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
   const dim3 grid(static_cast<unsigned>(ceil_div<long long>(M, kBM)), static_cast<unsigned>(splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
   int rc = check_launch("gemm_tf32x3_kernel<nt>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
-  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 256)), 256, 0, st>>>(workspace, C, mn, splits);
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 64)), 256, 0, st>>>(workspace, C, mn, splits);
   return check_launch("splitk_reduce_kernel");
 }
 
@@ -416,14 +440,14 @@ TRL_API int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
-  GemmParams p{splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
+  GemmParams p{nullptr, 0, splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
   const dim3 grid(static_cast<unsigned>(M / kBM), static_cast<unsigned>(splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
   int rc = check_launch("gemm_tf32x3_kernel<tn>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
-  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 256)), 256, 0, st>>>(workspace, C, mn, splits);
+  splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 64)), 256, 0, st>>>(workspace, C, mn, splits);
   return check_launch("splitk_reduce_kernel");
 }
 

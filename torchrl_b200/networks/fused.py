@@ -69,6 +69,8 @@ def wgrad(gz, x, out=None):
         if ws is None:
             ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
         return ops.gemm_tf32x3_tn(gz, x, out=out, splits=64, workspace=ws)
+    if _MATMUL_MODE != "fp32" and K <= 32 and _skinny_ok(gz) and (out is None or out.is_contiguous()):
+        return skinny_tn(gz, x, out=out)                 # (H,K) = gz^T x, first-layer weight gradient
     if H < 4 or M < 4096:
         return torch.mm(gz.t(), x, out=out) if out is not None else torch.mm(gz.t(), x)
     S = 16 if min(H, K) >= 128 else 64
@@ -145,13 +147,60 @@ class _Workspace:
         return ws
 
 
+_SKINNY_MIN_ROWS = 1024
+_SKINNY = False        # csrc/skinny.cu layers: correct but (round 1) not faster than cuBLAS -> opt-in, see set_skinny
+_TN_WS = {}
+
+
+def set_skinny(flag):
+    """Route the first (K = obs_dim) and output (N <= 8) Linear layers through csrc/skinny.cu.  Measured on B200 at
+    M = 16384 (gpurun_out/torch_prof_tc3.txt): k_fwd 20.5 us (cuBLAS + epilogue 20), n_fwd 9.3 (8.9), n_dgrad 8.0
+    (7.4), tn wgrad 55 / 23 us (bmm split-K 19 / 17) -- no win yet, so the default stays cuBLAS."""
+    global _SKINNY
+    _SKINNY = bool(flag)
+
+
+def _skinny_ok(x):
+    return _SKINNY and _ENABLED and x.is_cuda and x.shape[0] >= _SKINNY_MIN_ROWS
+
+
+def skinny_tn(a, b, out=None, colsum=None, out_transposed=False):
+    """out = a^T @ b for a (M,H), b (M,K<=32) [+ colsum = b.sum(0)]: csrc/skinny.cu, two deterministic stages."""
+    M, H = a.shape
+    K = b.shape[1]
+    key = (M, H, K, str(a.device))
+    ws = _TN_WS.get(key)
+    if ws is None:
+        n = int(_lib.load().trl_skinny_tn_scratch_floats(M, H, K))
+        ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((K, H) if out_transposed else (H, K), dtype=torch.float32, device=a.device)
+    _lib.call("trl_skinny_tn", ops._chk(a, torch.float32, "a"), ops._chk(b, torch.float32, "b"),
+              ops._chk(out, torch.float32, "out"), None if colsum is None else ops._chk(colsum, torch.float32, "colsum"),
+              M, H, K, int(bool(out_transposed)), ws.data_ptr(), ops._stream())
+    _lib.add_launches(1)
+    return out
+
+
 class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         tc = (_MATMUL_MODE == "tf32x3" and min(x.shape[0], x.shape[1], weight.shape[0]) >= _TF32X3_MIN_DIM)
-        if _tc3_ok(x.shape[0], weight.shape[0], x.shape[1]) and weight.is_contiguous():
-            z = ops.gemm_tf32x3_nt(x, weight)                  # tcgen05: x (M,K) . W (256,K)^T
+        if (_MATMUL_MODE != "fp32" and _skinny_ok(x) and x.shape[1] <= 64 and weight.shape[0] % 4 == 0
+                and weight.is_contiguous() and bias.is_contiguous()):
+            # skinny first layer: GEMM + bias + activation in one memory-bound launch
+            z = torch.empty(x.shape[0], weight.shape[0], dtype=torch.float32, device=x.device)
+            _lib.call("trl_skinny_k_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), z.data_ptr(), x.shape[0],
+                      x.shape[1], weight.shape[0], act, ops._stream())
             ctx.save_for_backward(x, weight, z)
+            ctx.act, ctx.tc, ctx.params = act, False, (weight, bias)
+            return z
+        if _tc3_ok(x.shape[0], weight.shape[0], x.shape[1]) and weight.is_contiguous():
+            # tcgen05: act(x (M,K) . W (256,K)^T + b), bias + activation fused into the TMEM epilogue
+            z = ops.gemm_tf32x3_nt(x, weight, bias=bias, act=act)
+            ctx.save_for_backward(x, weight, z)
+            ctx.act, ctx.tc, ctx.params = act, False, (weight, bias)
+            return z
         elif tc:
             x_hi, x_lo = split_tf32(x)
             w_hi, w_lo = split_tf32(weight)
@@ -217,6 +266,13 @@ class _LinearPlain(torch.autograd.Function):
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
         ctx.params = (weight, bias)
+        N, H = weight.shape
+        ctx.skinny = (_MATMUL_MODE != "fp32" and _skinny_ok(x) and N <= 8 and H % 4 == 0 and weight.is_contiguous())
+        if ctx.skinny:
+            y = torch.empty(x.shape[0], N, dtype=torch.float32, device=x.device)
+            _lib.call("trl_skinny_n_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), x.shape[0], H, N,
+                      ops._stream())
+            return y
         return torch.addmm(bias, x, weight.t())
 
     @staticmethod
@@ -225,6 +281,16 @@ class _LinearPlain(torch.autograd.Function):
         g = g if g.is_contiguous() else g.contiguous()
         w_param, b_param = ctx.params
         db_out, dw_out = _grad_out(b_param), _grad_out(w_param)
+        if ctx.skinny:
+            N, H = weight.shape
+            dx = None
+            if ctx.needs_input_grad[0]:
+                dx = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
+                _lib.call("trl_skinny_n_dgrad", g.data_ptr(), weight.data_ptr(), dx.data_ptr(), x.shape[0], H, N,
+                          ops._stream())
+            db = db_out if db_out is not None else torch.empty(N, dtype=torch.float32, device=x.device)
+            dw = skinny_tn(x, g, out=dw_out, colsum=db, out_transposed=True)     # dW (N,H) = g^T x, db = sum g
+            return dx, None if dw_out is not None else dw, None if db_out is not None else db
         dx = torch.mm(g, weight) if ctx.needs_input_grad[0] else None
         dw = wgrad(g, x, out=dw_out) if ctx.needs_input_grad[1] else None
         db = None

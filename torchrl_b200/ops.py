@@ -397,7 +397,7 @@ def per_insert(prio, row_ptr, max_prio):
 
 
 # ------------------------------------------------------------------------------------------ tensor-core GEMM
-def gemm_tf32x3_nt(a, b, out=None, splits=1, workspace=None):
+def gemm_tf32x3_nt(a, b, out=None, splits=1, workspace=None, bias=None, act=0):
     """out (M,256) = a (M,K) @ b (256,K)^T on the tcgen05 tensor cores with 3xTF32 error compensation
     (csrc/gemm_tf32x3.cu).  a, b contiguous fp32, K % (32*splits) == 0."""
     M, K = a.shape
@@ -407,7 +407,7 @@ def gemm_tf32x3_nt(a, b, out=None, splits=1, workspace=None):
     if splits > 1 and workspace is None:
         workspace = torch.empty(splits * M * 256, dtype=F32, device=a.device)
     _lib.call("trl_gemm_tf32x3_nt", _chk(a, F32, "a"), _chk(b, F32, "b"), _chk(out, F32, "out"), M, K, int(splits),
-              None if workspace is None else workspace.data_ptr(), _stream())
+              None if workspace is None else workspace.data_ptr(), _opt(bias, F32, "bias"), int(act), _stream())
     if splits > 1:
         _lib.add_launches(1)      # + the split-K reduction launch
     return out
