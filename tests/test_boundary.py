@@ -53,6 +53,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     from torchrl_b200 import _lib
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setenv("TORCHRL_B200_NO_AUTOBUILD", "1")
     import pytest
     with pytest.raises(_lib.NativeLibraryError):
         _lib.load()

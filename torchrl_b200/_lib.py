@@ -95,6 +95,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and os.environ.get("TORCHRL_B200_NO_AUTOBUILD") != "1":
+        try:                                    # nvcc is part of the image: compile in-tree on first use
+            from . import build as _build
+            _build.build()
+        except Exception as e:                  # noqa: BLE001
+            raise NativeLibraryError("%s not found and the in-tree nvcc build failed (%s); there is no CPU "
+                                     "fallback" % (LIB_PATH, e)) from e
     if not os.path.exists(LIB_PATH):
         raise NativeLibraryError(
             "%s not found: build it with `python -m torchrl_b200.build` (there is no CPU fallback)" % LIB_PATH)
