@@ -204,6 +204,16 @@ int trl_skinny_n_fwd(const float* X, const float* W, const float* bias, float* Y
                      void* stream);                                   /* Y = X W^T + b, N <= 8 */
 int trl_skinny_n_dgrad(const float* G, const float* W, float* dX, int64_t M, int H, int N, void* stream);
 
+/* ---- K1 for BASELINE config 4: synthetic Atari-shaped pixel env, obs (N,4,84,84) uint8, 6 actions (defined in
+ * oracle/synth_atari.py; the reference only wraps real ALE games, env/atari_wrapper.py).  latent: (N,5) int32. */
+int trl_synth_atari_step(uint8_t* obs, int* latent, const float* actions, int* elapsed, float* reward,
+                         uint8_t* done, uint8_t* time_limit, int64_t N, int max_steps, void* stream);
+int trl_synth_atari_reset(uint8_t* obs, int* latent, int* elapsed, unsigned* episode, const unsigned* seeds,
+                          const uint8_t* mask, const int* zero_is_mask, int episode_bias, int bump, int64_t N,
+                          void* stream);
+/* ScaledFloatFrame (env/atari_wrapper.py:171-180): out = in * scale */
+int trl_u8_to_f32(const uint8_t* in, float* out, int64_t n, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,136 @@
+"""BASELINE config 4 pieces: synthetic Atari-shaped pixel env (bit-exact vs oracle/synth_atari.py), the uint8
+pixel collector, and DQN / QR-DQN (+ prioritised replay) training on it."""
+import numpy as np
+import pytest
+
+from oracle import synth_atari as oa
+
+
+def test_oracle_game_rules():
+    lat = {"bx": np.array([10, 40]), "by": np.array([73, 73]), "vx": np.array([1, -1]), "vy": np.array([2, 2]),
+           "px": np.array([8, 60])}
+    new, r, miss = oa.step_latent(lat, np.array([0, 0]))
+    assert list(r) == [1, -1] and list(miss) == [False, True]          # env 0 hits the paddle, env 1 misses
+    assert new["vy"][0] == -2 and new["by"][0] == 2 * 74 - 75
+    fr = oa.render(new)
+    assert fr.shape == (2, 84, 84) and fr.dtype == np.uint8 and fr.max() == 255 and (fr == 200).sum() == 2 * 24
+
+
+@pytest.mark.gpu
+def test_atari_env_bit_exact_vs_oracle():
+    import torch
+    from torchrl_b200.env import get_vec_env
+    N = 37
+    env = get_vec_env("SynthAtari-v0", {}, N)
+    env.seed(9)
+    obs = env.reset().cpu().numpy()
+    seeds = ((9 * N + np.arange(N)) & 0xFFFFFFFF).astype(np.uint64)
+    episodes = np.zeros(N, dtype=np.uint64)
+    lat = oa.reset_latent(seeds, episodes)
+    np.testing.assert_array_equal(env.latent.cpu().numpy(), np.stack([lat[k] for k in ("bx", "by", "vx", "vy", "px")], 1))
+    stack = np.repeat(oa.render(lat)[:, None], 4, axis=1)
+    np.testing.assert_array_equal(obs, stack)
+    rs = np.random.RandomState(0)
+    elapsed = np.zeros(N, dtype=np.int64)
+    n_done = 0
+    for t in range(300):
+        act = rs.randint(0, 6, N)
+        lat, r, miss = oa.step_latent(lat, act)
+        elapsed += 1
+        stack = np.concatenate([stack[:, 1:], oa.render(lat)[:, None]], axis=1)
+        o, rew, dn, info = env.step(torch.from_numpy(act).cuda())
+        np.testing.assert_array_equal(o.cpu().numpy(), stack)
+        np.testing.assert_array_equal(rew.cpu().numpy()[:, 0], r.astype(np.float32))
+        np.testing.assert_array_equal(dn.cpu().numpy()[:, 0], miss)
+        assert not info["time_limit"].any()
+        if miss.any():                                   # partial reset of the finished envs, like the collectors
+            n_done += int(miss.sum())
+            episodes[miss] += 1
+            fresh = oa.reset_latent(seeds[miss], episodes[miss])
+            for k in lat:
+                lat[k][miss] = fresh[k]
+            stack[miss] = np.repeat(oa.render(fresh)[:, None], 4, axis=1)
+            elapsed[miss] = 0
+            o = env.partial_reset(dn.squeeze(-1))
+            np.testing.assert_array_equal(o.cpu().numpy(), stack)
+    assert n_done > 0
+    f = env.to_float(env.obs)
+    np.testing.assert_allclose(f.cpu().numpy(), stack.astype(np.float32) / 255.0, rtol=1e-6)
+
+
+def _build_pixel(kind, N=16, rows=24, use_graph=True, prioritized=False):
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    import torchrl_b200.policies as policies
+    from torchrl_b200.algo import DQN, QRDQN
+    from torchrl_b200.collector import PixelVecCollector
+    from torchrl_b200.env import get_vec_env
+    from torchrl_b200.replay_buffers import BaseReplayBuffer, PrioritizedReplayBuffer
+    from torchrl_b200.utils import NullLogger
+    dev = torch.device("cuda:0")
+    env = get_vec_env("SynthAtari-v0", {}, N)
+    eval_env = get_vec_env("SynthAtari-v0", {}, N)
+    env.seed(0); torch.manual_seed(0); np.random.seed(0)
+    Q = 11 if kind == "qrdqn" else 1
+    buf = (PrioritizedReplayBuffer if prioritized else BaseReplayBuffer)(env_nums=N, max_replay_buffer_size=rows * N)
+    qf = networks.Net(input_shape=(4, 84, 84), output_shape=6 * Q,
+                      hidden_shapes=[[16, [8, 8], [4, 4], [0, 0]], [32, [4, 4], [2, 2], [0, 0]]],
+                      append_hidden_shapes=[64], base_type=networks.CNNBase, activation_func=nn.ReLU)
+    if kind == "qrdqn":
+        pf = policies.EpsilonGreedyQRDQNDiscretePolicy(quantile_num=Q, qf=qf, start_epsilon=0.5, end_epsilon=0.1,
+                                                       decay_frames=100, action_shape=6)
+    else:
+        pf = policies.EpsilonGreedyDQNDiscretePolicy(qf=qf, start_epsilon=0.5, end_epsilon=0.1, decay_frames=100,
+                                                     action_shape=6)
+    col = PixelVecCollector(env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device=dev, epoch_frames=8 * N,
+                            max_episode_frames=30, use_cuda_graph=use_graph)
+    common = dict(qf=qf, pf=pf, qlr=1e-3, optimizer_info={"eps": 1e-4}, env=env, replay_buffer=buf, collector=col,
+                  logger=NullLogger(), discount=0.99, batch_size=4 * N, device=dev, save_dir=None, opt_times=4,
+                  use_soft_update=False, target_hard_update_period=3, pretrain_epochs=1, num_epochs=2,
+                  use_cuda_graph=use_graph)
+    agent = QRDQN(quantile_num=Q, **common) if kind == "qrdqn" else DQN(**common)
+    return agent, col, buf, env
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["dqn", "qrdqn"])
+def test_pixel_collector_and_dqn_training(kind):
+    import torch
+    agent, col, buf, env = _build_pixel(kind)
+    agent.pretrain()
+    for epoch in range(2):
+        agent.current_epoch = epoch
+        col.train_one_epoch()
+        agent.update_per_epoch()
+        for info in agent._last_infos:
+            assert np.isfinite(info["Training/qf_loss"]) and np.isfinite(info["q_s_a"])
+    assert buf._obs.dtype == torch.uint8 and buf._obs.shape == (24, 16, 4, 84, 84) and buf._size == 24
+    obs, nxt = buf._obs.cpu().numpy(), buf._next_obs.cpu().numpy()
+    term = buf._terminals.cpu().numpy()[..., 0].astype(bool)
+    for t in range(23):
+        # frame-stack property of every stored transition, and continuity where no reset happened
+        np.testing.assert_array_equal(nxt[t][:, :3], obs[t][:, 1:])
+        cont = ~term[t]
+        same = (obs[t + 1][cont] == nxt[t][cont]).reshape(cont.sum(), -1).all(axis=1)
+        assert same.mean() > 0.9                      # the rest were reset by the 30-frame collector timeout
+    acts = buf._acts.cpu().numpy()
+    assert acts.min() >= 0 and acts.max() <= 5 and np.all(acts == np.round(acts))
+    assert 0.1 <= agent.pf.epsilon < 0.5             # schedule advanced on the host, fed through a device scalar
+
+
+@pytest.mark.gpu
+def test_qrdqn_with_prioritized_replay_on_pixels():
+    """Config 4 end to end: QR-DQN heads + prioritised row sampling with importance weights on uint8 frames."""
+    import torch
+    agent, col, buf, env = _build_pixel("qrdqn", prioritized=True, use_graph=False)
+    agent.pretrain()
+    col.train_one_epoch()
+    np.random.seed(3)
+    batch = buf.random_batch(4 * 16, agent.sample_key)
+    assert batch["obs"].dtype == torch.uint8 and batch["weights"].shape == (64, 1)
+    info = agent.update({k: batch[k] for k in agent.sample_key})
+    assert np.isfinite(info["Training/qf_loss"])
+    td = torch.randn(64, 1, device="cuda")
+    buf.update_priorities(batch["indices"], td)
+    assert float(buf._priorities.max()) > 0

@@ -68,6 +68,9 @@ SIGNATURES = {
     "trl_skinny_tn": [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
     "trl_skinny_n_fwd": [vp, vp, vp, vp, i64, i32, i32, vp],
     "trl_skinny_n_dgrad": [vp, vp, vp, i64, i32, i32, vp],
+    "trl_synth_atari_step": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
+    "trl_synth_atari_reset": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
+    "trl_u8_to_f32": [vp, vp, i64, f32, vp],
     "trl_offpolicy_scratch_doubles": [i64],
     "trl_td_target": [vp, vp, vp, vp, vp, vp, f32, f32, i64, vp, vp, vp, vp, vp],
     "trl_td3_smooth_action": [vp, vp, f32, f32, u64, vp, i64, vp, vp],

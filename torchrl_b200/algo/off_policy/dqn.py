@@ -41,7 +41,10 @@ class DQN(OffRLAlgo):
         return self.opt.data
 
     def _prep_obs(self, x):
+        """uint8 frames -> float32 * obs_scale (ScaledFloatFrame) in one launch; float inputs pass through."""
         if x.dtype == torch.uint8:
+            if hasattr(self.env, "to_float") and x.is_contiguous() and x.numel() % 4 == 0:
+                return self.env.to_float(x)
             x = x.float()
             if self.obs_scale:
                 x = x * self.obs_scale

@@ -58,8 +58,11 @@ class VecCollector:
         a = self.env.action_space.shape[0] if self.continuous else 1
         self._N, self._o, self._a = N, o, a
         dev = self.device
-        self.current_ob = torch.empty(N, o, dtype=F32, device=dev)
-        self.current_ob.copy_(self.env.reset())
+        if getattr(self.env, "pixel", False):
+            self.current_ob = self.env.reset()               # uint8 frame stack, updated in place by the env
+        else:
+            self.current_ob = torch.empty(N, o, dtype=F32, device=dev)
+            self.current_ob.copy_(self.env.reset())
         self.current_step = torch.zeros(N, dtype=I32, device=dev)
         self.train_rew = torch.zeros(N, dtype=F64, device=dev)
         self._epoch_reward = torch.zeros(N, dtype=F64, device=dev)

@@ -8,6 +8,7 @@ import torch
 
 from . import synth_spec
 from .synth import SynthVecEnv
+from .synth_atari import SynthAtariVecEnv, ENV_ID as ATARI_ID
 
 
 def _device(device):
@@ -21,6 +22,8 @@ def _device(device):
 def get_vec_env(env_id, env_param, vec_env_nums, device=None, **kwargs):
     if synth_spec.is_synth(env_id):
         return SynthVecEnv(env_id, vec_env_nums, env_param, device=_device(device), **kwargs)
+    if env_id == ATARI_ID:
+        return SynthAtariVecEnv(vec_env_nums, env_param, device=_device(device), **kwargs)
     raise NotImplementedError("only the synthetic device envs are built in this round: %r" % (env_id,))
 
 

@@ -50,8 +50,15 @@ class EpsilonGreedyDQNDiscretePolicy:
         else:
             self.epsilon = self.end_epsilon
 
-    def explore(self, x):
+    def tick(self):
+        """Advance the epsilon schedule by one step (host).  Collectors that replay a captured step graph call
+        this outside the graph and pass the value through a device scalar (`explore(x, epsilon=tensor)`)."""
         self._anneal()
+
+    def explore(self, x, epsilon=None):
+        if epsilon is None:
+            self._anneal()
+            epsilon = self.epsilon
         x = x.squeeze(0)
         output = self.qf(x)
         action = self.q_to_a(output)
@@ -61,7 +68,7 @@ class EpsilonGreedyDQNDiscretePolicy:
         else:
             r = torch.rand(action.shape, device=x.device)
             random_action = torch.randint(0, self.action_shape, action.shape, device=x.device)
-        action = torch.where(r < self.epsilon, random_action, action)
+        action = torch.where(r < epsilon, random_action, action)
         return {"q_value": output, "action": action}
 
     def eval_act(self, x):
