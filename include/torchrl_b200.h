@@ -159,8 +159,9 @@ int trl_twin_mse_loss(const float* q1, const float* q2, const float* y, int64_t 
                       float* info2, double* scratch, unsigned* ticket, void* stream);
 /* fused QR-DQN / DQN loss incl. greedy target selection; info3 = [loss, mean q_s_a, mean reward] */
 int trl_qr_dqn_loss(const float* pred, const float* next, const float* actions, const float* rewards,
-                    const uint8_t* terminals, int B, int n_actions, int n_quantiles, float gamma, float kappa,
-                    int mse, float* grad, float* info3, double* scratch, unsigned* ticket, void* stream);
+                    const uint8_t* terminals, const float* weights, int B, int n_actions, int n_quantiles,
+                    float gamma, float kappa, int mse, float* grad, float* td_out, float* info3, double* scratch,
+                    unsigned* ticket, void* stream);   /* weights / td_out: prioritised replay (may be NULL) */
 
 /* ---- MLP epilogues around the cuBLAS GEMMs of MLPBase (networks/base.py:24-44): z <- act(z + b) in place
  * (act: 0 none, 1 tanh, 2 relu) and its backward g_pre = g * act'(out), dbias = column sums (one launch each). */

@@ -123,14 +123,14 @@ def test_pixel_collector_and_dqn_training(kind):
 def test_qrdqn_with_prioritized_replay_on_pixels():
     """Config 4 end to end: QR-DQN heads + prioritised row sampling with importance weights on uint8 frames."""
     import torch
-    agent, col, buf, env = _build_pixel("qrdqn", prioritized=True, use_graph=False)
+    agent, col, buf, env = _build_pixel("qrdqn", prioritized=True, use_graph=True)
     agent.pretrain()
     col.train_one_epoch()
+    assert torch.all(buf._priorities[:16] == 1.0)            # collector-written rows entered with the max priority
     np.random.seed(3)
     batch = buf.random_batch(4 * 16, agent.sample_key)
     assert batch["obs"].dtype == torch.uint8 and batch["weights"].shape == (64, 1)
-    info = agent.update({k: batch[k] for k in agent.sample_key})
-    assert np.isfinite(info["Training/qf_loss"])
-    td = torch.randn(64, 1, device="cuda")
-    buf.update_priorities(batch["indices"], td)
-    assert float(buf._priorities.max()) > 0
+    before = buf._priorities.clone()
+    agent.update_per_epoch()                                 # prioritised path: sample, weighted loss, new priorities
+    assert len(agent._last_infos) == 4 and all(np.isfinite(i["Training/qf_loss"]) for i in agent._last_infos)
+    assert not torch.equal(before, buf._priorities) and float(buf._priorities[:16].min()) > 0

@@ -64,8 +64,12 @@ class DQN(OffRLAlgo):
             next_q = self.target_qf(next_obs).contiguous()
         A = q_pred.shape[-1] // self.quantile_num
         pred = q_pred if q_pred.is_contiguous() else q_pred.contiguous()
+        weights = batch.get("weights")                 # prioritised replay: importance weights, TD magnitudes out
+        self._td = torch.empty(B, dtype=torch.float32, device=obs.device) if weights is not None else None
         grad, _ = ops.qr_dqn_loss(pred, next_q, acts.contiguous(), rewards, terminals, self.discount, ub["scratch"],
-                                  A, self.quantile_num, mse=self._mse, info=info[0:3])
+                                  A, self.quantile_num, mse=self._mse, info=info[0:3],
+                                  weights=None if weights is None else weights.reshape(-1).contiguous(),
+                                  td_out=self._td)
         torch.autograd.backward([pred], [grad])
         self.opt.step()
         self._update_target_networks()

@@ -90,9 +90,38 @@ class OffRLAlgo(RLAlgo):
         self._maybe_hard_update()
         return v
 
+    def _update_per_epoch_prioritized(self, flush_infos):
+        """Prioritised replay (no reference counterpart): per update draw rows proportionally to their
+        priority, weight the loss by the importance weights and write the new |TD| priorities back.
+        Round 1: eager launches (the sampler consumes host uniforms per update)."""
+        rb = self.replay_buffer
+        infos = []
+        for _ in range(self.opt_times):
+            batch = rb.random_batch(self.batch_size, self.sample_key)
+            self.training_update_num += 1
+            variant = self._variant()
+            self._explicit_batch = batch
+            try:
+                self._update_body(variant)
+                self._maybe_hard_update()
+            finally:
+                self._explicit_batch = None
+            td = getattr(self, "_td", None)
+            if td is not None:
+                rb.update_priorities(batch["indices"], td)
+            if flush_infos:
+                infos.append(self._decode_info(self._ub["info"][0].cpu().numpy(), variant))
+        if flush_infos:
+            self._last_infos = infos
+            if self.logger is not None:
+                for info in infos:
+                    self.logger.add_update_info(info)
+
     def update_per_epoch(self, flush_infos=True):
         """opt_times x {random_batch; update} (off_rl_algo.py:46-51)."""
         ub = self._ub or self._ub_setup()
+        if hasattr(self.replay_buffer, "update_priorities"):
+            return self._update_per_epoch_prioritized(flush_infos)
         size = self.replay_buffer.num_steps_can_sample()
         for u in range(ub["U"]):
             idx = np.random.randint(0, size, ub["b"])           # one draw per update, like random_batch

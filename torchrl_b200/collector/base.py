@@ -134,6 +134,8 @@ class VecCollector:
                 self._v_next.copy_(self.vf(self.env.obs_out).reshape(-1))
                 v_next = self._v_next
             self._finalize(v_next)
+            if hasattr(self.replay_buffer, "mark_inserted"):
+                self.replay_buffer.mark_inserted()    # prioritised ring: the new row enters with the max priority
             ops.counter_advance(None, self.replay_buffer._top_dev, self._T, self.replay_buffer._size_dev)
 
     def _need_bootstrap(self):

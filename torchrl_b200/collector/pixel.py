@@ -68,6 +68,8 @@ class PixelVecCollector(VecCollector):
             # envs whose collector step counter was just zeroed need a fresh episode (done or timeout); the
             # finalize kernel already advanced their episode counter
             env._reset(zero_is_mask=self.current_step, episode_bias=1, bump=0)
+            if hasattr(rb, "mark_inserted"):
+                rb.mark_inserted()                    # prioritised ring: the new row enters with the max priority
             ops.counter_advance(None, rb._top_dev, self._T, rb._size_dev)
 
     def _need_bootstrap(self):

@@ -278,6 +278,8 @@ struct QrParams {
   const float* __restrict__ actions;    // (B) action index stored as float
   const float* __restrict__ rewards;    // (B)
   const uint8_t* __restrict__ terminals;// (B)
+  const float* __restrict__ weights;    // (B) importance weights (prioritised replay) or nullptr
+  float* __restrict__ td_out;           // (B) per-sample loss magnitude (new priority signal) or nullptr
   float* __restrict__ grad;             // (B, A, Q)
   float* __restrict__ info;             // [0] loss [1] mean q_s_a [2] mean reward
   double* __restrict__ partial;         // (B, 3)
@@ -325,7 +327,8 @@ __global__ void __launch_bounds__(kOffThreads) qr_loss_kernel(const QrParams p) 
   }
   __syncthreads();
   double lsum = 0.0, qsum = 0.0;
-  const float scale = 1.0f / (static_cast<float>(p.B) * static_cast<float>(Q) * static_cast<float>(Q));
+  const float wb = p.weights ? p.weights[b] : 1.0f;       // importance weight of this sample
+  const float scale = wb / (static_cast<float>(p.B) * static_cast<float>(Q) * static_cast<float>(Q));
   for (int i = tid; i < Q; i += nthr) {
     const float th = s_theta[i];
     qsum += th;
@@ -333,7 +336,7 @@ __global__ void __launch_bounds__(kOffThreads) qr_loss_kernel(const QrParams p) 
     if (p.mse) {
       const float d = th - s_y[0];
       lsum += static_cast<double>(d) * d;
-      g = 2.f * d / static_cast<float>(p.B);
+      g = 2.f * d * wb / static_cast<float>(p.B);
     } else {
       const float tau = (2.f * i + 1.f) / (2.f * Q);
       float acc_l = 0.f, acc_g = 0.f;
@@ -352,7 +355,11 @@ __global__ void __launch_bounds__(kOffThreads) qr_loss_kernel(const QrParams p) 
     gb[act * Q + i] = g;
   }
   double v = blk_sum(lsum, shd);
-  if (tid == 0) p.partial[3 * b] = v;
+  if (tid == 0) {
+    p.partial[3 * b] = v * wb;
+    // un-weighted per-sample loss magnitude: |TD| for DQN, mean quantile-Huber loss for QR-DQN
+    if (p.td_out) p.td_out[b] = p.mse ? sqrtf(static_cast<float>(v)) : static_cast<float>(v / (static_cast<double>(Q) * Q));
+  }
   v = blk_sum(qsum, shd);
   if (tid == 0) { p.partial[3 * b + 1] = v; p.partial[3 * b + 2] = r; }
   if (last_cta(p.ticket) && tid == 0) {
@@ -436,14 +443,15 @@ TRL_API int trl_twin_mse_loss(const float* q1, const float* q2, const float* y, 
 }
 
 TRL_API int trl_qr_dqn_loss(const float* pred, const float* next, const float* actions, const float* rewards,
-                            const uint8_t* terminals, int B, int n_actions, int n_quantiles, float gamma, float kappa,
-                            int mse, float* grad, float* info3, double* scratch, unsigned* ticket, void* stream) {
+                            const uint8_t* terminals, const float* weights, int B, int n_actions, int n_quantiles,
+                            float gamma, float kappa, int mse, float* grad, float* td_out, float* info3,
+                            double* scratch, unsigned* ticket, void* stream) {
   using namespace trl;
   TRL_REQUIRE(B >= 1 && n_actions >= 1 && n_quantiles >= 1, "trl_qr_dqn_loss: bad sizes");
   TRL_REQUIRE(!mse || n_quantiles == 1, "trl_qr_dqn_loss: the DQN (mse) form needs n_quantiles == 1");
   TRL_REQUIRE(pred && next && actions && rewards && terminals && grad && info3 && scratch && ticket,
               "trl_qr_dqn_loss: null pointer");
-  QrParams p{pred, next, actions, rewards, terminals, grad, info3, scratch, ticket, B, n_actions, n_quantiles, gamma,
+  QrParams p{pred, next, actions, rewards, terminals, weights, td_out, grad, info3, scratch, ticket, B, n_actions, n_quantiles, gamma,
              kappa, mse};
   const size_t smem = sizeof(float) * (2 * n_quantiles + n_actions);
   TRL_REQUIRE(smem <= 48 * 1024, "trl_qr_dqn_loss: %d quantiles x %d actions exceed shared memory", n_quantiles,

@@ -356,7 +356,7 @@ def twin_mse_loss(q1, q2, y, scratch, info=None):
 
 
 def qr_dqn_loss(pred, nxt, actions, rewards, terminals, gamma, scratch, n_actions, n_quantiles, mse=False, kappa=1.0,
-                info=None):
+                info=None, weights=None, td_out=None):
     """Fused (QR-)DQN loss: quantile-Huber (qrdqn.py:36-60, utils.py:5-13) or squared TD error (dqn.py:53-60);
     returns d loss / d pred with the shape of pred and info = [loss, mean q_s_a, mean reward]."""
     B = rewards.numel()
@@ -364,8 +364,9 @@ def qr_dqn_loss(pred, nxt, actions, rewards, terminals, gamma, scratch, n_action
     if info is None:
         info = torch.zeros(3, dtype=F32, device=pred.device)
     _lib.call("trl_qr_dqn_loss", _chk(pred, F32, "pred"), _chk(nxt, F32, "next"), _chk(actions, F32, "actions"),
-              _chk(rewards, F32, "rewards"), _chk(terminals, U8, "terminals"), B, int(n_actions), int(n_quantiles),
-              float(gamma), float(kappa), int(bool(mse)), _chk(grad, F32, "grad"), _chk(info, F32, "info"),
+              _chk(rewards, F32, "rewards"), _chk(terminals, U8, "terminals"), _opt(weights, F32, "weights"), B,
+              int(n_actions), int(n_quantiles), float(gamma), float(kappa), int(bool(mse)), _chk(grad, F32, "grad"),
+              _opt(td_out, F32, "td_out"), _chk(info, F32, "info"),
               scratch.buf[4].data_ptr(), scratch.t(4), _stream())
     return grad, info
 
