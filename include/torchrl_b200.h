@@ -108,6 +108,10 @@ int trl_ring_write(int nkeys, const void* const* src, void* const* dst, const in
                    const int* row_ptr, void* stream);
 /* mean, unbiased std, max, min of a vector (algo/on_policy/ppo.py:141-147). */
 int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream);
+/* K12: the same statistics over the union of all ranks' minibatches: local raw moments [sum, sumsq, max, -min]
+ * (fp64) -> one all-gather -> combine. */
+int trl_vec_moments(const float* x, int64_t n, double* moments4, void* stream);
+int trl_vec_stats_from_moments(const double* gathered, int world, double n_total, float* stats4, void* stream);
 
 /* ---- K8: PPO losses, value + gradient wrt the network outputs (algo/on_policy/ppo.py:41-122). */
 int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim);

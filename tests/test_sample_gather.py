@@ -196,3 +196,16 @@ def test_prioritized_buffer_api():
     for _ in range(50):
         hits += int((buf.random_batch(4 * N, ["obs"])["indices"] == int(rows[0])).any().item())
     assert hits >= 25                                                           # high-priority row is drawn often
+
+
+@pytest.mark.gpu
+def test_global_vec_stats_single_rank_matches_vec_stats():
+    """The K12 statistics path (raw moments -> gather -> combine) equals the single-launch statistics."""
+    import torch
+    from torchrl_b200 import ops
+    from torchrl_b200.distributed import DataParallelContext
+    ctx = DataParallelContext(backend="nccl")
+    x = torch.randn(16384, device="cuda") * 2 - 0.5
+    out = torch.zeros(4, device="cuda")
+    ctx.global_vec_stats(x, out)
+    torch.testing.assert_close(out, ops.vec_stats(x), rtol=1e-6, atol=1e-7)

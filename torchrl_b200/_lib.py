@@ -45,6 +45,8 @@ SIGNATURES = {
     "trl_row_gather": [i32, vp, vp, vp, vp, vp, i32, vp],
     "trl_ring_write": [i32, vp, vp, vp, vp, vp],
     "trl_vec_stats": [vp, i64, vp, vp],
+    "trl_vec_moments": [vp, i64, vp, vp],
+    "trl_vec_stats_from_moments": [vp, i32, f64, vp, vp],
     "trl_ppo_actor_scratch_doubles": [i64, i32],
     "trl_ppo_actor_loss": [vp, vp, i32, vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
     "trl_ppo_critic_loss": [vp, vp, vp, i64, i32, f32, vp, vp, vp, vp, vp],

@@ -94,6 +94,49 @@ __global__ void __launch_bounds__(1024) vec_stats_kernel(const float* __restrict
   }
 }
 
+// raw moments of x[0..n): m[0..3] = sum, sum of squares, max, -min (fp64) -- the local half of a
+// cross-rank statistic (K12: advantage normalisation over all ranks' envs, ppo.py:147)
+__global__ void __launch_bounds__(1024) vec_moments_kernel(const float* __restrict__ x, long long n,
+                                                          double* __restrict__ m) {
+  __shared__ double sh_s[32], sh_q[32];
+  __shared__ float sh_mx[32], sh_mn[32];
+  double s = 0.0, q = 0.0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[i];
+    s += v; q += static_cast<double>(v) * v;
+    mx = fmaxf(mx, v); mn = fminf(mn, v);
+  }
+  s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sh_s[wid] = s; sh_q[wid] = q; sh_mx[wid] = mx; sh_mn[wid] = mn; }
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < nw ? sh_s[lane] : 0.0; q = lane < nw ? sh_q[lane] : 0.0;
+    mx = lane < nw ? sh_mx[lane] : -INFINITY; mn = lane < nw ? sh_mn[lane] : INFINITY;
+    s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+    if (lane == 0) { m[0] = s; m[1] = q; m[2] = mx; m[3] = -static_cast<double>(mn); }
+  }
+}
+
+// combine W ranks' raw moments (W x 4 doubles, rank order) into [mean, unbiased std, max, min]
+__global__ void vec_stats_from_moments_kernel(const double* __restrict__ g, int W, double n_total,
+                                              float* __restrict__ stats) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double s = 0.0, q = 0.0, mx = -INFINITY, nmn = -INFINITY;
+  for (int r = 0; r < W; ++r) {
+    s += g[4 * r]; q += g[4 * r + 1];
+    mx = fmax(mx, g[4 * r + 2]); nmn = fmax(nmn, g[4 * r + 3]);
+  }
+  const double mean = s / n_total;
+  double var = (q - s * mean) / (n_total - 1.0);
+  if (var < 0.0) var = 0.0;
+  stats[0] = static_cast<float>(mean);
+  stats[1] = static_cast<float>(sqrt(var));
+  stats[2] = static_cast<float>(mx);
+  stats[3] = static_cast<float>(-nmn);
+}
+
 }  // namespace trl
 
 static int launch_row_copy(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
@@ -146,4 +189,20 @@ TRL_API int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream
   TRL_REQUIRE(x && stats4, "trl_vec_stats: null pointer");
   vec_stats_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n, stats4);
   return check_launch("vec_stats_kernel");
+}
+
+TRL_API int trl_vec_moments(const float* x, int64_t n, double* moments4, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(n >= 1, "trl_vec_moments: need at least one element");
+  TRL_REQUIRE(x && moments4, "trl_vec_moments: null pointer");
+  vec_moments_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(x, n, moments4);
+  return check_launch("vec_moments_kernel");
+}
+
+TRL_API int trl_vec_stats_from_moments(const double* gathered, int world, double n_total, float* stats4, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(world >= 1 && n_total >= 1, "trl_vec_stats_from_moments: bad sizes");
+  TRL_REQUIRE(gathered && stats4, "trl_vec_stats_from_moments: null pointer");
+  vec_stats_from_moments_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, n_total, stats4);
+  return check_launch("vec_stats_from_moments_kernel");
 }

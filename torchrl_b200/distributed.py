@@ -83,8 +83,22 @@ class DataParallelContext:
         return t
 
     def global_vec_stats(self, x, out):
-        """out[0..3] = mean, unbiased std, max, min of the concatenation of `x` over all ranks (every
-        rank holds the same number of elements).  Device-only: capturable in a CUDA graph."""
+        """out[0..3] = mean, unbiased std, max, min of the concatenation of `x` over all ranks (every rank holds
+        the same number of elements).  CUDA: one raw-moments launch, ONE all-gather of 4 doubles per rank, one
+        combine launch (capturable).  CPU tensors (gloo tests): the same arithmetic in torch ops."""
+        if x.is_cuda:
+            from . import _lib, ops
+            if not hasattr(self, "_mom"):
+                self._mom = torch.zeros(4, dtype=torch.float64, device=x.device)
+                self._mom_all = torch.zeros(4 * self.world_size, dtype=torch.float64, device=x.device)
+            _lib.call("trl_vec_moments", ops._chk(x, torch.float32, "x"), x.numel(), self._mom.data_ptr(), ops._stream())
+            if self.active:
+                dist.all_gather_into_tensor(self._mom_all, self._mom)
+            else:
+                self._mom_all.copy_(self._mom)
+            _lib.call("trl_vec_stats_from_moments", self._mom_all.data_ptr(), self.world_size,
+                      float(x.numel() * self.world_size), ops._chk(out, torch.float32, "stats"), ops._stream())
+            return out
         xd = x.double()
         mom = torch.stack([xd.sum(), (xd * xd).sum()])
         ext = torch.stack([x.max(), -x.min()]).double()
