@@ -86,7 +86,9 @@ int trl_tanh_gaussian_sample_bwd(const float* action, const float* eps, const fl
                                  int tanh_action, float* g_mean, float* g_log_std, void* stream);
 
 /* ---- K4/K5: per-step rollout store + timeout bootstrap + partial reset
- * (collector/on_policy.py:115-153, collector/base.py:204-228, replay_buffers/base.py:19-37). */
+ * (collector/on_policy.py:115-153, collector/base.py:204-228, replay_buffers/base.py:19-37).
+ * state/elapsed/episode/seeds all NULL = host envs behind the pinned-memory bridge: rows are
+ * stored and counters updated, the masked reset itself is done by the host env afterwards. */
 int trl_collect_finalize(const float* cur_ob_in, const float* next_norm, float* state, const float* act,
                          const float* value, const float* v_next, const float* reward, const uint8_t* done,
                          const uint8_t* tl, int* elapsed, unsigned* episode, const unsigned* seeds,

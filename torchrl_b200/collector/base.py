@@ -31,6 +31,7 @@ class VecCollector:
         self.pf = pf
         self.replay_buffer = replay_buffer
         self.env = env
+        self._host_env = bool(getattr(env, "host_bridge", False))
         self.env.train()
         self.continuous = is_box(self.env.action_space)
         self.train_render = train_render
@@ -73,6 +74,7 @@ class VecCollector:
         self._v_next = torch.zeros(N, dtype=F32, device=dev) if self.on_policy else None
         self._eps = None
         self._host_step = 0
+        self._host_steps = np.zeros(N, dtype=np.int64)      # host mirror of current_step (host envs only)
         self._graphs = {}
         self._eager_steps = 0
         self._alloc_buffer()
@@ -106,12 +108,15 @@ class VecCollector:
     def _finalize(self, v_next):
         env, rb = self.env, self.replay_buffer
         nrm = env._obs_normalizer if getattr(env, "obs_norm", False) else None
-        _lib.call("trl_collect_finalize", self.current_ob.data_ptr(), env.obs_out.data_ptr(), env.state.data_ptr(),
+        ext = self._host_env            # host envs: the kernel stores rows / counters, the host env resets
+        _lib.call("trl_collect_finalize", self.current_ob.data_ptr(), env.obs_out.data_ptr(),
+                  None if ext else env.state.data_ptr(),
                   self._act.data_ptr(), None if self._value is None else self._value.data_ptr(),
                   None if v_next is None else v_next.data_ptr(), env.reward.data_ptr(), env.done.data_ptr(),
-                  env.time_limit.data_ptr(), env.elapsed.data_ptr(), env.episode.data_ptr(), env.seeds.data_ptr(),
+                  env.time_limit.data_ptr(), None if ext else env.elapsed.data_ptr(),
+                  None if ext else env.episode.data_ptr(), None if ext else env.seeds.data_ptr(),
                   self.current_step.data_ptr(), self.train_rew.data_ptr(), self._epoch_reward.data_ptr(),
-                  self._ret_log.data_ptr(), self._n_done.data_ptr(), env.any_reset.data_ptr(),
+                  self._ret_log.data_ptr(), self._n_done.data_ptr(), None if ext else env.any_reset.data_ptr(),
                   None if nrm is None else nrm._mean.data_ptr(), None if nrm is None else nrm._var.data_ptr(),
                   self.current_ob.data_ptr(), rb._obs.data_ptr(), rb._next_obs.data_ptr(), rb._acts.data_ptr(),
                   rb._values.data_ptr() if self.on_policy else None, rb._rewards.data_ptr(),
@@ -138,6 +143,38 @@ class VecCollector:
                 self.replay_buffer.mark_inserted()    # prioritised ring: the new row enters with the max priority
             ops.counter_advance(None, self.replay_buffer._top_dev, self._T, self.replay_buffer._size_dev)
 
+    def _step_host(self):
+        """One collector step over HOST envs behind env/bridge.py.  Same order of
+        operations as the reference loop (collector/on_policy.py:94-153): act, step, bootstrap the envs cut
+        by `max_episode_frames`, store the row, reset finished envs.  Eager: the host env sits in the middle."""
+        env = self.env
+        with torch.no_grad():
+            ob = self.current_ob
+            self._policy_action(ob)
+            if self.on_policy:
+                self._value.copy_(self.vf(ob).reshape(-1))
+            env.launch_step(self._act)
+            sc = self._host_steps + 1
+            mask = env.host_done | (sc >= self.max_episode_frames)
+            reset = bool(mask.any())
+            v_next = None
+            if self.on_policy and reset:
+                self._v_next.copy_(self.vf(env.obs_out).reshape(-1))
+                v_next = self._v_next
+            self._finalize(v_next)
+            if reset:
+                raw = env.partial_reset(mask)
+                if self.reference_quirks or not env.obs_norm:
+                    self.current_ob.copy_(raw)              # quirk A.1: raw observations for ALL envs
+                else:
+                    m = torch.from_numpy(mask).to(self.device)
+                    self.current_ob[m] = env._obs_normalizer.filt(raw)[m]
+            self._host_steps = np.where(mask, 0, sc)
+            if hasattr(self.replay_buffer, "mark_inserted"):
+                self.replay_buffer.mark_inserted()
+            ops.counter_advance(None, self.replay_buffer._top_dev, self._T, self.replay_buffer._size_dev)
+        self.replay_buffer.advance_host(1)
+
     def _need_bootstrap(self):
         """Host-side prediction of `any(done) or any(current_step >= max_episode_frames)` for this
         step (collector/on_policy.py:132-133).  Exact for lock-step envs (episode ends depend only
@@ -163,6 +200,12 @@ class VecCollector:
         self.replay_buffer.advance_host(1)
 
     def _step(self):
+        if self._host_env:
+            if D.get_noise_mode() == "reference_cpu" and self.continuous and hasattr(self.pf, "act_only"):
+                if self._eps is None:
+                    self._eps = torch.empty(self._N, self._a, dtype=F32, device=self.device)
+                self._eps.copy_(D.draw_reference_noise((self._N, self._a), self.device))
+            return self._step_host()
         boot = self._need_bootstrap()
         if D.get_noise_mode() == "reference_cpu" and self.continuous and hasattr(self.pf, "act_only"):
             eps = D.draw_reference_noise((self._N, self._a), self.device)

@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(256) collect_finalize_kernel(const FinalizePar
     p.b_time_limits[row] = p.tl[n];
     if (p.b_values) p.b_values[row] = p.value[n];
     p.step_count[n] = mask ? 0 : sc;
-    if (mask) { p.elapsed[n] = 0; }
+    if (mask && p.elapsed) { p.elapsed[n] = 0; }
     s_mask[tid] = mask ? 1 : 0;
   }
   __syncthreads();
@@ -214,6 +214,12 @@ __global__ void __launch_bounds__(256) collect_finalize_kernel(const FinalizePar
     for (int i = tid; i < ne * a; i += nthr) p.b_acts[dsta + i] = p.act[srca + i];
   }
   __syncthreads();  // cur_ob_in may alias cur_ob_out: finish every read before the writes below
+  if (!p.seeds) {
+    // external (host) envs: the reset happens on the host after this launch (env/bridge.py); carry the
+    // stepped observation forward and let the bridge overwrite the rows it resets
+    for (int i = tid; i < ne * o; i += nthr) p.cur_ob_out[env_base * o + i] = p.next_norm[env_base * o + i];
+    return;
+  }
   // partial reset + next current_ob
   for (int i = tid; i < ne * o; i += nthr) {
     const int e = i / o, j = i - e * o;
@@ -296,10 +302,13 @@ TRL_API int trl_collect_finalize(const float* cur_ob_in, const float* next_norm,
   using namespace trl;
   TRL_REQUIRE(N >= 0 && obs_dim >= 1 && act_dim >= 1, "trl_collect_finalize: bad sizes");
   if (N == 0) return TRL_OK;
-  TRL_REQUIRE(cur_ob_in && next_norm && state && act && reward && done && tl && elapsed && episode && seeds &&
-                  step_count && ep_return && epoch_reward && n_done && cur_ob_out && b_obs && b_next_obs && b_acts &&
-                  b_rewards && b_terminals && b_time_limits && t_ptr,
+  TRL_REQUIRE(cur_ob_in && next_norm && act && reward && done && tl && step_count && ep_return && epoch_reward &&
+                  n_done && cur_ob_out && b_obs && b_next_obs && b_acts && b_rewards && b_terminals && b_time_limits &&
+                  t_ptr,
               "trl_collect_finalize: null pointer");
+  TRL_REQUIRE((state && elapsed && episode && seeds) || (!state && !elapsed && !episode && !seeds),
+              "trl_collect_finalize: state/elapsed/episode/seeds must be all given (device env, in-kernel reset) "
+              "or all NULL (host env, external reset)");
   TRL_REQUIRE(!b_values || value, "trl_collect_finalize: b_values given without value");
   FinalizeParams p{cur_ob_in, next_norm, state, act, value, v_next, reward, done, tl, elapsed, episode, seeds,
                    step_count, ep_return, epoch_reward, ret_log, n_done, any_reset, norm_mean, norm_var, cur_ob_out,
