@@ -526,3 +526,39 @@ class TD3Port:
             info["new_actions/max"] = new_actions.max().item()
             info["new_actions/min"] = new_actions.min().item()
         return info
+
+
+class DDPGPort:
+    """DDPG.update (algo/off_policy/ddpg.py:40-111): deterministic policy gradient through the critic, one
+    critic regressed on r + (1-d)*gamma*Q'(s', pi'(s')), actor step before critic step, Polyak targets."""
+
+    def __init__(self, pf, qf, plr=3e-4, qlr=3e-4, discount=0.99, tau=0.005):
+        self.pf, self.qf = pf, qf
+        self.tpf, self.tqf = copy.deepcopy(pf), copy.deepcopy(qf)
+        self.pf_opt = torch.optim.Adam(pf.parameters(), lr=plr)
+        self.qf_opt = torch.optim.Adam(qf.parameters(), lr=qlr)
+        self.discount, self.tau = discount, tau
+
+    def update(self, batch):
+        obs = torch.Tensor(batch["obs"])
+        actions = torch.Tensor(batch["acts"])
+        next_obs = torch.Tensor(batch["next_obs"])
+        rewards = torch.Tensor(batch["rewards"])
+        terminals = torch.Tensor(batch["terminals"])
+        new_actions = self.pf(obs)
+        policy_loss = -self.qf([obs, new_actions]).mean()
+        target_q = self.tqf([next_obs, self.tpf(next_obs)])
+        q_target = rewards + (1.0 - terminals) * self.discount * target_q
+        qf_loss = nn.functional.mse_loss(self.qf([obs, actions]), q_target.detach())
+        self.pf_opt.zero_grad()
+        policy_loss.backward()
+        self.pf_opt.step()
+        self.qf_opt.zero_grad()
+        qf_loss.backward()
+        self.qf_opt.step()
+        _polyak(self.pf, self.tpf, self.tau)
+        _polyak(self.qf, self.tqf, self.tau)
+        return {"Reward_Mean": rewards.mean().item(), "Training/policy_loss": policy_loss.item(),
+                "Training/qf_loss": qf_loss.item(), "new_actions/mean": new_actions.mean().item(),
+                "new_actions/std": new_actions.std().item(), "new_actions/max": new_actions.max().item(),
+                "new_actions/min": new_actions.min().item()}

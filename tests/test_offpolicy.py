@@ -326,3 +326,45 @@ def test_qrdqn_agent_update_runs_and_matches_restatement():
     # greedy action for a batch of envs (the reference's .item() version only handles one env, A.5)
     acts = pf.eval_act(torch.randn(5, o, device="cuda"))
     assert acts.shape == (5, 1)
+
+
+@pytest.mark.gpu
+def test_ddpg_update_matches_reference_port():
+    """DDPG on the off-policy kernels vs the oracle port (pinned bit-exact to the reference's DDPG.update by
+    tests/test_oracle_vs_reference.py): logged scalars and all parameters after 4 updates."""
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    import torchrl_b200.policies as policies
+    from oracle import ref_port
+    from torchrl_b200.algo import DDPG
+    from tests.test_oracle_vs_reference import _offpolicy_batches
+    o, a, hidden, B, seed = 11, 3, (24, 24), 48, 4
+    batches = _offpolicy_batches(o, a, B, 4, seed)
+    torch.set_num_threads(4)
+    torch.manual_seed(seed)
+    ppf = ref_port.FixedNoisePolicy(o, a, list(hidden), nn.ReLU, norm_std_explore=0.1, tanh_action=True)
+    pq = ref_port.QNet(o + a, 1, list(hidden), nn.ReLU)
+    port = ref_port.DDPGPort(ppf, pq, plr=1e-3, qlr=1e-3)
+    port_infos = [port.update(b) for b in batches]
+    torch.manual_seed(seed)
+    net = dict(hidden_shapes=list(hidden), append_hidden_shapes=[], base_type=networks.MLPBase,
+               activation_func=nn.ReLU)
+    pf = policies.DetContPolicy(input_shape=o, output_shape=a, tanh_action=True, **net)
+    qf = networks.QNet(input_shape=o + a, output_shape=1, **net)
+
+    class _RB:
+        env_nums = 1
+    agent = DDPG(pf=pf, qf=qf, plr=1e-3, qlr=1e-3, env=_Env(o, a), replay_buffer=_RB(), collector=_Col(),
+                 logger=None, discount=0.99, batch_size=B, device="cuda:0", save_dir=None, tau=0.005,
+                 use_soft_update=True, use_cuda_graph=False)
+    infos = [agent.update(b) for b in batches]
+    for u, (mine, ref) in enumerate(zip(infos, port_infos)):
+        assert mine.keys() == ref.keys(), (mine.keys(), ref.keys())
+        for k, v in ref.items():
+            assert abs(mine[k] - v) <= 2e-3 * abs(v) + 2e-4, (u, k, mine[k], v)
+    mine = torch.cat([p.detach().reshape(-1) for n in (agent.pf, agent.qf, agent.target_pf, agent.target_qf)
+                      for p in n.parameters()]).cpu().numpy()
+    ref = torch.cat([p.detach().reshape(-1) for n in (port.pf, port.qf, port.tpf, port.tqf)
+                     for p in n.parameters()]).numpy()
+    np.testing.assert_allclose(mine, ref, atol=2e-4)

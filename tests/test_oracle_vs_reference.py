@@ -205,3 +205,37 @@ def test_port_reproduces_reference_offpolicy_updates(tmp_path, kind):
     assert len(ref_params) == len(port_params)
     for x, y in zip(ref_params, port_params):
         np.testing.assert_array_equal(x, y)
+
+
+def test_port_reproduces_reference_ddpg_updates(tmp_path):
+    import torch
+    import torch.nn as nn
+    from oracle import reference_loader, ref_port
+    reference_loader.load()
+    import torchrl.networks as networks
+    import torchrl.policies as policies
+    from torchrl.algo.off_policy.ddpg import DDPG
+    o, a, hidden, B, seed = 11, 3, (24, 24), 48, 4
+    batches = _offpolicy_batches(o, a, B, 4, seed)
+    torch.manual_seed(seed)
+    net = dict(hidden_shapes=list(hidden), append_hidden_shapes=[], base_type=networks.MLPBase,
+               activation_func=torch.nn.ReLU)
+    pf = policies.DetContPolicy(input_shape=o, output_shape=a, tanh_action=True, **net)
+    qf = networks.QNet(input_shape=o + a, output_shape=1, **net)
+    ref = DDPG(pf=pf, qf=qf, plr=1e-3, qlr=1e-3, env=_FakeEnv(o, a), replay_buffer=None, collector=_FakeCollector(),
+               logger=None, discount=0.99, batch_size=B, device="cpu", save_dir=str(tmp_path), tau=0.005,
+               use_soft_update=True)
+    ref_infos = [ref.update(b) for b in batches]
+    ref_params = [p.detach().numpy().copy() for n_ in ref.networks for p in n_.parameters()]
+    torch.manual_seed(seed)
+    ppf = ref_port.FixedNoisePolicy(o, a, list(hidden), nn.ReLU, norm_std_explore=0.1, tanh_action=True)
+    pq = ref_port.QNet(o + a, 1, list(hidden), nn.ReLU)
+    port = ref_port.DDPGPort(ppf, pq, plr=1e-3, qlr=1e-3)
+    port_infos = [port.update(b) for b in batches]
+    port_params = [p.detach().numpy() for n_ in (port.pf, port.qf, port.tpf, port.tqf) for p in n_.parameters()]
+    for x, y in zip(ref_infos, port_infos):
+        assert x.keys() == y.keys()
+        for k in x:
+            assert x[k] == y[k], k
+    for x, y in zip(ref_params, port_params):
+        np.testing.assert_array_equal(x, y)

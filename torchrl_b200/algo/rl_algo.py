@@ -44,7 +44,7 @@ class SegmentOptimizer:
 class RLAlgo:
     def __init__(self, env=None, replay_buffer=None, collector=None, logger=None, grad_clip=None, discount=0.99,
                  num_epochs=3000, batch_size=128, device='cpu', save_interval=100, eval_interval=1, save_dir=None,
-                 use_cuda_graph=True, dist=None):
+                 use_cuda_graph=True, dist=None, resume_checkpoints=False):
         self.env = env
         self.continuous = is_box(self.env.action_space)
         self.replay_buffer = replay_buffer
@@ -74,6 +74,21 @@ class RLAlgo:
         self.use_cuda_graph = bool(use_cuda_graph)
         self.dist = dist                    # None or a torchrl_b200.distributed.DataParallelContext
         self.current_epoch = 0
+        self.first_epoch = 0                # load_checkpoint moves it past the last finished epoch
+        self.resume_checkpoints = bool(resume_checkpoints)
+
+    # ------------------------------------------------------------------ resume (absent in the reference)
+    def save_checkpoint(self, path):
+        """Full training state (weights, Adam moments, targets, collector / env / normaliser state, replay
+        ring, every RNG stream): see utils/checkpoint.py."""
+        from ..utils.checkpoint import save_checkpoint
+        return save_checkpoint(self, path)
+
+    def load_checkpoint(self, path):
+        """Restore a `save_checkpoint` file in place; `train()` then continues with the next epoch."""
+        from ..utils.checkpoint import load_checkpoint
+        self.first_epoch = load_checkpoint(self, path) + 1
+        return self.first_epoch
 
     def start_epoch(self):
         pass
@@ -103,7 +118,7 @@ class RLAlgo:
         if hasattr(self, "pretrain_frames"):
             total_frames = self.pretrain_frames
         self.start_epoch()
-        for epoch in range(self.num_epochs):
+        for epoch in range(self.first_epoch, self.num_epochs):
             self.current_epoch = epoch
             self.start_epoch()
 
@@ -149,6 +164,8 @@ class RLAlgo:
 
             if epoch % self.save_interval == 0:
                 self.snapshot(self.save_dir, epoch)
+                if self.resume_checkpoints and self.save_dir is not None:
+                    self.save_checkpoint(osp.join(self.save_dir, "checkpoint_latest.pt"))
 
         self.snapshot(self.save_dir, "finish")
         self.collector.terminate()
