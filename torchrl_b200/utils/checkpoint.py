@@ -18,6 +18,7 @@ _AGENT_SCALARS = ("current_epoch", "training_update_num", "best_eval", "pretrain
 _COLLECTOR_SCALARS = ("_host_step", "_host_steps")
 _ENV_SCALARS = ("_host_elapsed", "_host_mirror_ok", "training")
 _BUFFER_SCALARS = ("_top", "_size")
+_POLICY_SCALARS = ("count", "epsilon")                 # epsilon-greedy schedule position
 _OPT_TENSORS = ("exp_avg", "exp_avg_sq", "step_counts", "lr_host", "lr")
 
 
@@ -31,13 +32,19 @@ def _scalars(obj, names):
 
 
 def _rng_holders(agent):
+    """(name, _DeviceRng) of every device Philox stream the run consumes.  Policies create theirs lazily on
+    the first sampling launch, so a freshly built agent is asked to create it now."""
     out = []
     for name in ("pf", "target_pf"):
         m = getattr(agent, name, None)
-        if m is not None and getattr(m, "_rng", None) is not None:
-            out.append((name + "._rng", m._rng))
+        if m is None:
+            continue
+        if hasattr(m, "_rng_state"):
+            out.append((name + "._rng", m._rng_state(agent.device)))
+        elif getattr(m, "_rng", None) is not None:
+            out.append((name + "._rng", m._rng.ensure(agent.device)))
     if getattr(agent, "_rng", None) is not None:
-        out.append(("agent._rng", agent._rng))
+        out.append(("agent._rng", agent._rng.ensure(agent.device)))
     return out
 
 
@@ -53,6 +60,7 @@ def save_checkpoint(agent, path, include_replay=None):
     state["agent_scalars"] = _scalars(agent, _AGENT_SCALARS)
     state["episode_rewards"] = list(agent.episode_rewards)
     state["training_episode_rewards"] = list(agent.training_episode_rewards)
+    state["policy_scalars"] = _scalars(agent.pf, _POLICY_SCALARS)
     state["collector_tensors"] = _tensors(col)
     state["collector_scalars"] = _scalars(col, _COLLECTOR_SCALARS)
     state["env_tensors"] = _tensors(env)
@@ -105,7 +113,7 @@ def load_checkpoint(agent, path):
             _restore(env._obs_normalizer, state["normalizer"], "normalizer")
         _restore(rb, state["buffer_tensors"], "buffer")
     for obj, key in ((agent, "agent_scalars"), (col, "collector_scalars"), (env, "env_scalars"),
-                     (rb, "buffer_scalars")):
+                     (rb, "buffer_scalars"), (agent.pf, "policy_scalars")):
         for k, v in state[key].items():
             setattr(obj, k, v)
     agent.episode_rewards.clear()
