@@ -210,6 +210,13 @@ int trl_skinny_tn(const float* A, const float* B, float* Out, float* colsum, int
 int trl_skinny_n_fwd(const float* X, const float* W, const float* bias, float* Y, int64_t M, int H, int N,
                      void* stream);                                   /* Y = X W^T + b, N <= 8 */
 int trl_skinny_n_dgrad(const float* G, const float* W, float* dX, int64_t M, int H, int N, void* stream);
+/* backward fusions (autograd of networks/base.py:43-44 + nets.py:49-52): first-layer weight/bias gradient straight
+ * from the upstream gradient and the layer output; output-layer dgrad fused with the hidden activation backward. */
+int trl_skinny_act_wgrad(const float* G, const float* Y, const float* X, float* dW, float* db, int64_t M, int H,
+                         int K, int act, float* scratch, void* stream);
+int64_t trl_skinny_dgrad_act_scratch_floats(int64_t M, int H);
+int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* Y, float* gz, float* db, int64_t M, int H,
+                           int N, int act, float* scratch, void* stream);
 
 /* ---- K1 for BASELINE config 4: synthetic Atari-shaped pixel env, obs (N,4,84,84) uint8, 6 actions (defined in
  * oracle/synth_atari.py; the reference only wraps real ALE games, env/atari_wrapper.py).  latent: (N,5) int32. */

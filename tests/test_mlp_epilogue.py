@@ -140,9 +140,14 @@ def test_tc3_mlp_matches_fp32_mlp():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("inp,out,M", [(17, 6, 16384), (17, 1, 16384), (23, 1, 4096), (17, 8, 1500)])
-def test_skinny_layers_match_plain_torch(inp, out, M):
-    """First layer (K = obs_dim) and output layer (N = act_dim / 1) through csrc/skinny.cu vs cuBLAS."""
+@pytest.mark.parametrize("act_name", ["Tanh", "ReLU"])
+@pytest.mark.parametrize("inp,out,M,x_grad", [(17, 6, 16384, True), (17, 6, 16384, False), (17, 1, 16384, False),
+                                               (23, 1, 4096, True), (23, 8, 4100, False), (17, 8, 1500, False),
+                                               (5, 3, 9000, False)])
+def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
+    """First layer (K = obs_dim) and output layer (N = act_dim / 1) through csrc/skinny.cu vs cuBLAS, including
+    the two backward fusions: first-layer dW/db straight from (g, y) when the input needs no gradient, and the
+    output-layer dgrad fused with the hidden activation backward (M >= 8192: the _MLPTail node)."""
     import copy
     import torch
     import torch.nn as nn
@@ -150,25 +155,56 @@ def test_skinny_layers_match_plain_torch(inp, out, M):
     from torchrl_b200.networks import fused
     torch.manual_seed(inp * out)
     net = networks.Net(input_shape=inp, output_shape=out, hidden_shapes=[256, 256], append_hidden_shapes=[],
-                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+                       base_type=networks.MLPBase, activation_func=getattr(nn, act_name)).cuda()
     ref = copy.deepcopy(net)
-    x = torch.randn(M, inp, device="cuda", requires_grad=True)
-    x0 = x.detach().clone().requires_grad_()
+    x = torch.randn(M, inp, device="cuda", requires_grad=x_grad)
+    x0 = x.detach().clone().requires_grad_(x_grad)
     w = torch.randn(M, out, device="cuda")
-    fused.set_skinny(True)
-    try:
-        y1 = net(x)
-        (y1 * w).sum().backward()
-    finally:
-        fused.set_skinny(False)
+    assert fused._SKINNY                      # default route
+    y1 = net(x)
+    (y1 * w).sum().backward()
+    fused.set_skinny(False)
     fused.set_matmul_mode("fp32")
     try:
         y0 = ref(x0)
         (y0 * w).sum().backward()
     finally:
         fused.set_matmul_mode("tc3")
+        fused.set_skinny(True)
     torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
-    torch.testing.assert_close(x.grad, x0.grad, rtol=1e-4, atol=1e-5 * x0.grad.abs().max().item())
+    if act_name == "ReLU":
+        # relu'(y) = [y > 0] is discontinuous: a handful of the 4M hidden units sit within round-off of zero and
+        # switch side between the two summation orders; each flips one O(1) term of a gradient entry.  Require
+        # 99.8 % of the entries at the smooth-activation tolerance and bound the rest.
+        def close(a, b, scale, name):
+            err = (a - b).abs()
+            bad = err > (1e-4 * b.abs() + 2e-5 * scale)
+            assert bad.float().mean().item() < 2e-3, (name, bad.float().mean().item())
+            assert err.max().item() < 5e-2 * scale, (name, err.max().item(), scale)
+    else:
+        def close(a, b, scale, name):
+            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=name)
+    if x_grad:
+        close(x.grad, x0.grad, 0.5 * x0.grad.abs().max().item(), "x")
     for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
-        scale = p0.grad.abs().max().item() + 1e-12
-        torch.testing.assert_close(p1.grad, p0.grad, rtol=1e-4, atol=2e-5 * scale, msg=n1)
+        close(p1.grad, p0.grad, p0.grad.abs().max().item() + 1e-12, n1)
+
+
+@pytest.mark.gpu
+def test_skinny_backward_is_deterministic():
+    """Fixed combination order in every reduction: two runs give bit-identical gradients."""
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    torch.manual_seed(3)
+    net = networks.Net(input_shape=17, output_shape=6, hidden_shapes=[256, 256], append_hidden_shapes=[],
+                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+    x = torch.randn(16384, 17, device="cuda")
+    w = torch.randn(16384, 6, device="cuda")
+    grads = []
+    for _ in range(2):
+        net.zero_grad(set_to_none=True)
+        (net(x) * w).sum().backward()
+        grads.append([p.grad.clone() for p in net.parameters()])
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)

@@ -70,6 +70,9 @@ SIGNATURES = {
     "trl_skinny_tn": [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
     "trl_skinny_n_fwd": [vp, vp, vp, vp, i64, i32, i32, vp],
     "trl_skinny_n_dgrad": [vp, vp, vp, i64, i32, i32, vp],
+    "trl_skinny_act_wgrad": [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
+    "trl_skinny_dgrad_act_scratch_floats": [i64, i32],
+    "trl_skinny_n_dgrad_act": [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],
     "trl_synth_atari_step": [vp, vp, vp, vp, vp, vp, vp, i64, i32, vp],
     "trl_synth_atari_reset": [vp, vp, vp, vp, vp, vp, vp, i32, i32, i64, vp],
     "trl_u8_to_f32": [vp, vp, i64, f32, vp],
@@ -83,7 +86,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles": ctypes.c_int64,
              "trl_offpolicy_scratch_doubles": ctypes.c_int64, "trl_bias_act_bwd_scratch_floats": ctypes.c_int64,
-             "trl_skinny_tn_scratch_floats": ctypes.c_int64}
+             "trl_skinny_tn_scratch_floats": ctypes.c_int64,
+             "trl_skinny_dgrad_act_scratch_floats": ctypes.c_int64}
 # entry points that return a value rather than an error code
 _VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas",
                 "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")

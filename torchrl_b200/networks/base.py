@@ -52,12 +52,33 @@ class MLPBase(nn.Module):
     def forward(self, x):
         if self._pairs and fused.fused_enabled() and x.is_cuda:
             for fc, act in self._pairs:
-                if fused.can_fuse(x, fc, act):
-                    x = fused.linear_act(x, fc, fused.ACT_CODES[type(act)])
-                else:
-                    x = act(fc(x))
+                x = self._pair(x, fc, act)
             return x
         return self.seq_fcs(x)
+
+    @staticmethod
+    def _pair(x, fc, act):
+        if fused.can_fuse(x, fc, act):
+            return fused.linear_act(x, fc, fused.ACT_CODES[type(act)])
+        return act(fc(x))
+
+    def forward_with_head(self, x, head):
+        """head(self(x)) with the last hidden layer and the output layer as one fused autograd node when the
+        shapes allow (fused._MLPTail); None when they do not (the caller then takes the plain route)."""
+        if not (self._pairs and fused.fused_enabled() and x.is_cuda):
+            return None
+        for fc, act in self._pairs[:-1]:
+            x = self._pair(x, fc, act)
+        fc, act = self._pairs[-1]
+        if not fused.tail_ok(x, fc, act, head):
+            return head_plain(self._pair(x, fc, act), head)
+        return fused.mlp_tail(x, fc, fused.ACT_CODES[type(act)], head)
+
+
+def head_plain(h, head):
+    if h.is_cuda and h.dtype == torch.float32 and torch.is_grad_enabled():
+        return fused.linear_plain(h, head)
+    return head(h)
 
 
 def calc_next_shape(input_shape, conv_info):

@@ -69,7 +69,8 @@ def wgrad(gz, x, out=None):
         if ws is None:
             ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
         return ops.gemm_tf32x3_tn(gz, x, out=out, splits=64, workspace=ws)
-    if _MATMUL_MODE != "fp32" and K <= 32 and _skinny_ok(gz) and (out is None or out.is_contiguous()):
+    if (_MATMUL_MODE != "fp32" and K <= 24 and H % 32 == 0 and H <= 256 and _skinny_ok(gz)
+            and (out is None or out.is_contiguous())):
         return skinny_tn(gz, x, out=out)                 # (H,K) = gz^T x, first-layer weight gradient
     if H < 4 or M < 4096:
         return torch.mm(gz.t(), x, out=out) if out is not None else torch.mm(gz.t(), x)
@@ -148,14 +149,16 @@ class _Workspace:
 
 
 _SKINNY_MIN_ROWS = 1024
-_SKINNY = False        # csrc/skinny.cu layers: correct but (round 1) not faster than cuBLAS -> opt-in, see set_skinny
+_SKINNY = True         # csrc/skinny.cu serves the first (K = obs_dim) and output (N <= 8) layers
 _TN_WS = {}
 
 
 def set_skinny(flag):
-    """Route the first (K = obs_dim) and output (N <= 8) Linear layers through csrc/skinny.cu.  Measured on B200 at
-    M = 16384 (gpurun_out/torch_prof_tc3.txt): k_fwd 20.5 us (cuBLAS + epilogue 20), n_fwd 9.3 (8.9), n_dgrad 8.0
-    (7.4), tn wgrad 55 / 23 us (bmm split-K 19 / 17) -- no win yet, so the default stays cuBLAS."""
+    """Route the first (K = obs_dim <= 24) and output (N <= 8) Linear layers through csrc/skinny.cu (default on).
+    Measured on B200 at M = 16384, cold L2, including ~7 us of launch/event overhead (scripts/skinny_bench.py,
+    profiles/skinny_bench_r1.txt): k_fwd 18.5 us vs cuBLAS + epilogue 27.6; n_fwd 12.3 vs 23.2; n_dgrad 10.2 vs
+    12.3; output-layer wgrad + bias gradient 21.5 vs 35.9; first-layer wgrad 23.5 vs 23.6.  `set_skinny(False)`
+    restores cuBLAS for these layers."""
     global _SKINNY
     _SKINNY = bool(flag)
 
@@ -164,15 +167,20 @@ def _skinny_ok(x):
     return _SKINNY and _ENABLED and x.is_cuda and x.shape[0] >= _SKINNY_MIN_ROWS
 
 
+def _tn_scratch(M, H, K, device):
+    key = (M, H, K, str(device))
+    ws = _TN_WS.get(key)
+    if ws is None:
+        n = int(_lib.load().trl_skinny_tn_scratch_floats(M, H, K))
+        ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=device)
+    return ws
+
+
 def skinny_tn(a, b, out=None, colsum=None, out_transposed=False):
     """out = a^T @ b for a (M,H), b (M,K<=32) [+ colsum = b.sum(0)]: csrc/skinny.cu, two deterministic stages."""
     M, H = a.shape
     K = b.shape[1]
-    key = (M, H, K, str(a.device))
-    ws = _TN_WS.get(key)
-    if ws is None:
-        n = int(_lib.load().trl_skinny_tn_scratch_floats(M, H, K))
-        ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=a.device)
+    ws = _tn_scratch(M, H, K, a.device)
     if out is None:
         out = torch.empty((K, H) if out_transposed else (H, K), dtype=torch.float32, device=a.device)
     _lib.call("trl_skinny_tn", ops._chk(a, torch.float32, "a"), ops._chk(b, torch.float32, "b"),
@@ -186,8 +194,8 @@ class _LinearAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, act):
         tc = (_MATMUL_MODE == "tf32x3" and min(x.shape[0], x.shape[1], weight.shape[0]) >= _TF32X3_MIN_DIM)
-        if (_MATMUL_MODE != "fp32" and _skinny_ok(x) and x.shape[1] <= 64 and weight.shape[0] % 4 == 0
-                and weight.is_contiguous() and bias.is_contiguous()):
+        if (_MATMUL_MODE != "fp32" and _skinny_ok(x) and x.shape[1] <= 24 and weight.shape[0] % 4 == 0
+                and weight.shape[0] <= 1024 and weight.is_contiguous() and bias.is_contiguous()):
             # skinny first layer: GEMM + bias + activation in one memory-bound launch
             z = torch.empty(x.shape[0], weight.shape[0], dtype=torch.float32, device=x.device)
             _lib.call("trl_skinny_k_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), z.data_ptr(), x.shape[0],
@@ -223,10 +231,20 @@ class _LinearAct(torch.autograd.Function):
         x, weight, y = ctx.saved_tensors
         g = g if g.is_contiguous() else g.contiguous()
         M, H = y.shape
-        gz = torch.empty_like(y)
         w_param, b_param = ctx.params
         db_out, dw_out = _grad_out(b_param), _grad_out(w_param)
         db = db_out if db_out is not None else torch.empty(H, dtype=torch.float32, device=y.device)
+        K = x.shape[1]
+        if (not ctx.needs_input_grad[0] and _MATMUL_MODE != "fp32" and _skinny_ok(y) and K <= 24 and H % 32 == 0
+                and H <= 256 and x.is_contiguous() and (dw_out is None or dw_out.is_contiguous())):
+            # first layer (its input needs no gradient): dW and db straight from g and y in ONE pass over the
+            # (M, H) matrices; the activation gradient gz is never written to memory
+            dw = dw_out if dw_out is not None else torch.empty(H, K, dtype=torch.float32, device=y.device)
+            _lib.call("trl_skinny_act_wgrad", g.data_ptr(), y.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                      M, H, K, ctx.act, _tn_scratch(M, H, K, y.device).data_ptr(), ops._stream())
+            _lib.add_launches(1)
+            return None, None if dw_out is not None else dw, None if db_out is not None else db, None
+        gz = torch.empty_like(y)
         scratch, tickets = _Workspace.get(M, H, y.device)
         _lib.call("trl_bias_act_bwd", g.data_ptr(), y.data_ptr(), gz.data_ptr(), db.data_ptr(), M, H, ctx.act,
                   scratch.data_ptr(), tickets.data_ptr(), ops._stream())
@@ -267,7 +285,8 @@ class _LinearPlain(torch.autograd.Function):
         ctx.save_for_backward(x, weight)
         ctx.params = (weight, bias)
         N, H = weight.shape
-        ctx.skinny = (_MATMUL_MODE != "fp32" and _skinny_ok(x) and N <= 8 and H % 4 == 0 and weight.is_contiguous())
+        ctx.skinny = (_MATMUL_MODE != "fp32" and _skinny_ok(x) and N <= 8 and H in (128, 256)
+                      and weight.is_contiguous())
         if ctx.skinny:
             y = torch.empty(x.shape[0], N, dtype=torch.float32, device=x.device)
             _lib.call("trl_skinny_n_fwd", x.data_ptr(), weight.data_ptr(), bias.data_ptr(), y.data_ptr(), x.shape[0], H, N,
@@ -297,6 +316,74 @@ class _LinearPlain(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             db = torch.sum(g, 0, out=db_out) if db_out is not None else g.sum(0)
         return dx, None if dw_out is not None else dw, None if db_out is not None else db
+
+
+class _MLPTail(torch.autograd.Function):
+    """Last hidden layer + output layer of an MLP head as ONE autograd node:
+        y2 = act(x W2^T + b2)   (tcgen05 3xTF32, bias + activation in the TMEM epilogue)
+        out = y2 W3^T + b3      (csrc/skinny.cu n_fwd)
+    so that the backward can fuse the output-layer dgrad with the activation backward of the hidden layer
+    (trl_skinny_n_dgrad_act: gz2 and db2 in one pass, the (M, 256) dgrad matrix is never stored un-activated)."""
+
+    @staticmethod
+    def forward(ctx, x, w2, b2, w3, b3, act):
+        y2 = ops.gemm_tf32x3_nt(x, w2, bias=b2, act=act)
+        M, H = y2.shape
+        N = w3.shape[0]
+        out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        _lib.call("trl_skinny_n_fwd", y2.data_ptr(), w3.data_ptr(), b3.data_ptr(), out.data_ptr(), M, H, N,
+                  ops._stream())
+        ctx.save_for_backward(x, w2, y2, w3)
+        ctx.act = act
+        ctx.params = (w2, b2, w3, b3)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w2, y2, w3 = ctx.saved_tensors
+        g = g if g.is_contiguous() else g.contiguous()
+        M, H = y2.shape
+        N = w3.shape[0]
+        dev = y2.device
+        w2p, b2p, w3p, b3p = ctx.params
+        dw2_out, db2_out, dw3_out, db3_out = _grad_out(w2p), _grad_out(b2p), _grad_out(w3p), _grad_out(b3p)
+        db2 = db2_out if db2_out is not None else torch.empty(H, dtype=torch.float32, device=dev)
+        db3 = db3_out if db3_out is not None else torch.empty(N, dtype=torch.float32, device=dev)
+        gz = torch.empty_like(y2)
+        key = ("dgrad_act", M, H, str(dev))
+        ws = _TN_WS.get(key)
+        if ws is None:
+            n = int(_lib.load().trl_skinny_dgrad_act_scratch_floats(M, H))
+            ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("trl_skinny_n_dgrad_act", g.data_ptr(), w3.data_ptr(), y2.data_ptr(), gz.data_ptr(), db2.data_ptr(),
+                  M, H, N, ctx.act, ws.data_ptr(), ops._stream())
+        _lib.add_launches(1)
+        dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)      # dW3 (N,H) = g^T y2, db3 = sum g
+        dx = ops.gemm_tf32x3_nt(gz, ops.transpose_f32(w2)) if ctx.needs_input_grad[0] else None
+        dw2 = wgrad(gz, x, out=dw2_out)
+        return (dx, None if dw2_out is not None else dw2, None if db2_out is not None else db2,
+                None if dw3_out is not None else dw3, None if db3_out is not None else db3, None)
+
+
+def tail_ok(h, fc, act_module, head):
+    """True when `head(act(fc(h)))` can run as one _MLPTail node: 256-wide hidden layer on the tcgen05 kernel, an
+    output layer of at most 8 units, enough rows, gradients being recorded."""
+    if not (_ENABLED and _SKINNY and h.is_cuda and h.dtype == torch.float32 and torch.is_grad_enabled()):
+        return False
+    rows = h.numel() // h.shape[-1]
+    return (type(act_module) in ACT_CODES and rows >= max(_TC3_MIN_ROWS, _SKINNY_MIN_ROWS)
+            and _tc3_ok(rows, fc.out_features, fc.in_features) and head.in_features == fc.out_features
+            and head.out_features <= 8 and fc.bias is not None and head.bias is not None
+            and fc.weight.is_contiguous() and head.weight.is_contiguous())
+
+
+def mlp_tail(h, fc, act_code, head):
+    lead = h.shape[:-1]
+    h2 = h.reshape(-1, h.shape[-1])
+    if not h2.is_contiguous():
+        h2 = h2.contiguous()
+    out = _MLPTail.apply(h2, fc.weight, fc.bias, head.weight, head.bias, act_code)
+    return out.reshape(tuple(lead) + (out.shape[-1],))
 
 
 def linear_plain(x, fc):

@@ -46,8 +46,15 @@ class Net(nn.Module):
             return fused.linear_plain(h, self.append_fcs[0])
         return self.seq_append_fcs(h)
 
-    def forward(self, x):
+    def _trunk_head(self, x):
+        if len(self.append_fcs) == 1 and hasattr(self.base, "forward_with_head") and fused.fused_enabled():
+            out = self.base.forward_with_head(x, self.append_fcs[0])
+            if out is not None:
+                return out
         return self._head(self.base(x))
+
+    def forward(self, x):
+        return self._trunk_head(x)
 
 
 class FlattenNet(Net):
@@ -61,7 +68,7 @@ class QNet(Net):
     def forward(self, input):
         assert len(input) == 2, "Q Net only get observation and action"
         state, action = input
-        return self._head(self.base(torch.cat([state, action], dim=-1)))
+        return self._trunk_head(torch.cat([state, action], dim=-1))
 
 
 class BootstrappedNet(nn.Module):
