@@ -75,9 +75,11 @@ class ClockSampler:
         self.gpu = gpu_index
 
     def start(self):
+        if self.gpu is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -349,6 +351,9 @@ def run_ours(args):
             agent.update_per_epoch()
         else:
             col.rollout_no_sync()
+            if ctx.world_size > 1:
+                # keep the ranks' launch queues short and aligned before the collective-bearing update graphs
+                torch.cuda.current_stream(device).synchronize()
             agent.update_per_epoch(flush_infos=False)
 
     for _ in range(max(args.warmup, 3)):
@@ -358,7 +363,9 @@ def run_ours(args):
     torch.cuda.synchronize(device)
 
     # ---- value: device-timed, host out of the loop ------------------------------------------
-    sampler = ClockSampler(ctx.local_rank)
+    # one nvidia-smi poller for the whole job (rank 0's GPU): NVML queries take driver locks, and one poller per
+    # rank measurably stalled kernel launches at 4 ranks (value 266 ms/step vs 137 ms through the public API)
+    sampler = ClockSampler(ctx.local_rank if ctx.rank == 0 else None)
     launches0 = _lib.launch_count()
     ctx.barrier()
     torch.cuda.synchronize(device)
@@ -439,7 +446,7 @@ def run_ours(args):
                        "matmul": {"fp32": "fp32 cuBLAS SIMT (TF32 off)",
                                   "tf32x3": "3xTF32 error-compensated tensor-core GEMMs (fp32-faithful), cuBLAS",
                                   "tc3": "256-wide layers: hand-written tcgen05 3xTF32 GEMM (fp32-faithful, "
-                                         "csrc/gemm_tf32x3.cu); other layers fp32 cuBLAS SIMT"}[args.matmul], "cuda_graphs": not args.no_graph,
+                                         "csrc/gemm_tf32x3.cu); 17-wide / <=8-wide layers: HBM-bound fp32 kernels (csrc/skinny.cu)"}[args.matmul], "cuda_graphs": not args.no_graph,
                        "l2": "each step rewrites the whole 100 MB rollout working set and all activations "
                              "(> 126 MB L2 per epoch); the GAE roofline launch flushes L2 explicitly"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
