@@ -65,7 +65,11 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi poller (`-lms`) for SM clocks and throttle reasons.  It is STARTED BEFORE THE WARM-UP: the
+    start-up of nvidia-smi (NVML attaches every GPU of the box) was measured to stall CUDA launches once for
+    ~0.4 s in about one run out of three (value leg 199 ms/step instead of 118; 266 instead of 137 at 4 ranks),
+    which must not land inside the timed region.  Only the samples stamped inside [mark_begin, mark_end] count."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -73,6 +77,7 @@ class ClockSampler:
         self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
         self.proc = None
         self.gpu = gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         if self.gpu is None:
@@ -84,6 +89,20 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
@@ -93,22 +112,28 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows_in, rows_all = [], []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
+                if len(f) < 10:
                     continue
                 try:
-                    sm.append(float(f[1])); mx.append(float(f[2]))
+                    row = (float(f[2]), float(f[3]), f[6:10])
                 except ValueError:
                     continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                     f[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                rows_all.append(row)
+                ts = self._stamp(f[0])
+                if ts is not None and self.t0 is not None and self.t1 is not None and self.t0 <= ts <= self.t1 + 0.1:
+                    rows_in.append(row)
         except OSError:
             pass
+        sm, mx, reasons = [], [], set()
+        for clk, cmax, flags in (rows_in or rows_all):     # no stamped sample inside the region: keep them all
+            sm.append(clk); mx.append(cmax)
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
         if sm:
             sm.sort()
             out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
@@ -356,6 +381,10 @@ def run_ours(args):
                 torch.cuda.current_stream(device).synchronize()
             agent.update_per_epoch(flush_infos=False)
 
+    # one nvidia-smi poller for the whole job (rank 0's GPU), started now so that its start-up is over before
+    # the timed region (see ClockSampler)
+    sampler = ClockSampler(ctx.local_rank if ctx.rank == 0 else None)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         epoch(True)
     for _ in range(2):
@@ -363,13 +392,10 @@ def run_ours(args):
     torch.cuda.synchronize(device)
 
     # ---- value: device-timed, host out of the loop ------------------------------------------
-    # one nvidia-smi poller for the whole job (rank 0's GPU): NVML queries take driver locks, and one poller per
-    # rank measurably stalled kernel launches at 4 ranks (value 266 ms/step vs 137 ms through the public API)
-    sampler = ClockSampler(ctx.local_rank if ctx.rank == 0 else None)
     launches0 = _lib.launch_count()
     ctx.barrier()
     torch.cuda.synchronize(device)
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
@@ -380,6 +406,7 @@ def run_ours(args):
             torch.cuda.current_stream(device).synchronize()
     ev1.record()
     torch.cuda.synchronize(device)
+    sampler.mark_end()
     ctx.barrier()
     clocks = sampler.stop()
     t_dev = ctx.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)

@@ -173,14 +173,15 @@ def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
         fused.set_skinny(True)
     torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
     if act_name == "ReLU":
-        # relu'(y) = [y > 0] is discontinuous: a handful of the 4M hidden units sit within round-off of zero and
-        # switch side between the two summation orders; each flips one O(1) term of a gradient entry.  Require
-        # 99.8 % of the entries at the smooth-activation tolerance and bound the rest.
+        # relu'(y) = [y > 0] is discontinuous: a handful of the 4M hidden units sit within round-off of zero (the
+        # 3xTF32 tensor-core layer and the fp32 SIMT layer round differently) and switch side.  One switched unit
+        # changes that sample's whole back-propagated row, i.e. one of the M terms of EVERY entry of the earlier
+        # layers' weight gradients, so entry-wise tolerances at round-off level cannot hold.  A few rows out of
+        # M >= 1500 bound the relative Frobenius error by ~sqrt(flips / M) (a wrong mask or scale gives O(1)); the
+        # Tanh variants of this test hold the same kernels to round-off tolerances entry by entry.
         def close(a, b, scale, name):
-            err = (a - b).abs()
-            bad = err > (1e-4 * b.abs() + 2e-5 * scale)
-            assert bad.float().mean().item() < 2e-3, (name, bad.float().mean().item())
-            assert err.max().item() < 5e-2 * scale, (name, err.max().item(), scale)
+            rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
+            assert rel < 3e-2, (name, rel)
     else:
         def close(a, b, scale, name):
             torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=name)
