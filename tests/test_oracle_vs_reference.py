@@ -239,3 +239,33 @@ def test_port_reproduces_reference_ddpg_updates(tmp_path):
             assert x[k] == y[k], k
     for x, y in zip(ref_params, port_params):
         np.testing.assert_array_equal(x, y)
+
+
+def test_logger_files_match_reference(tmp_path, capsys):
+    """utils/logger.py:17-158: same log.csv (titles, per-epoch values, Mean/Std/Max/Min aggregation of the
+    per-update infos, "{:.5f}" formatting) and params.json from the product's Logger and the reference's."""
+    import json
+    from oracle import reference_loader
+    reference_loader.load()
+    from torchrl.utils.logger import Logger as RefLogger
+    from torchrl_b200.utils.logger import Logger
+    rs = np.random.RandomState(0)
+    updates = [[{"Training/policy_loss": rs.randn(), "Training/vf_loss": abs(rs.randn()), "ratio/max": 1 + rs.rand()}
+                for _ in range(5)] for _ in range(3)]
+    epochs = [{"Running_Average_Rewards": rs.randn() * 100, "Train_Epoch_Reward": rs.randn() * 1e3,
+               "eval_traj_length": 1000.0} for _ in range(3)]
+    out = {}
+    for name, cls in (("ref", RefLogger), ("mine", Logger)):
+        params = {"project": "p", "env_name": "SynthHalfCheetah-v0", "general_setting": {"discount": 0.99}}
+        lg = cls("exp", "SynthHalfCheetah-v0", 3, params, log_dir=str(tmp_path / name))
+        for e in range(3):
+            for info in updates[e]:
+                lg.add_update_info(info)
+            lg.add_epoch_info(e, (e + 1) * 4096, 1.5 * (e + 1), epochs[e])
+        lg.finish()
+        d = tmp_path / name / "exp" / "SynthHalfCheetah-v0" / "3"
+        out[name] = (open(d / "log.csv").read(), json.load(open(d / "params.json")))
+    capsys.readouterr()
+    assert out["mine"][0] == out["ref"][0]
+    assert out["mine"][1] == out["ref"][1]
+    assert out["ref"][0].count("\n") == 4 and "Training/policy_loss_Std" in out["ref"][0]
