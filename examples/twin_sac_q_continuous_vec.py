@@ -1,57 +1,28 @@
-"""Twin-Q SAC on a device-resident vectorised env -- counterpart of the reference's
-examples/twin_sac_q_continuous_vec.py (same flags / JSON schema / wiring).
+"""Twin-Q soft actor-critic on a device-resident vectorised env -- the torchrl_b200 counterpart of the reference's
+examples/twin_sac_q_continuous_vec.py (same flags, same JSON schema).
 
     python examples/twin_sac_q_continuous_vec.py --config config/twin_sac_q_synth_ant.json --vec_env_nums 1024
 """
-import os
-import os.path as osp
-import random
-import sys
-
-import numpy as np
 import torch
 
-sys.path.append(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-import torchrl_b200.networks as networks  # noqa: E402
-import torchrl_b200.policies as policies  # noqa: E402
-from torchrl_b200.algo import TwinSACQ  # noqa: E402
-from torchrl_b200.collector.base import VecCollector  # noqa: E402
-from torchrl_b200.env import get_vec_env  # noqa: E402
-from torchrl_b200.replay_buffers import BaseReplayBuffer  # noqa: E402
-from torchrl_b200.utils import Logger, get_args, get_params  # noqa: E402
+from _common import Run, main  # noqa: F401  (also puts the repository root on sys.path)
+import torchrl_b200.networks as networks
+import torchrl_b200.policies as policies
+from torchrl_b200.algo import TwinSACQ
+from torchrl_b200.collector import VecCollector
+from torchrl_b200.replay_buffers import BaseReplayBuffer
 
 
-def experiment(args, params):
-    if not args.cuda:
-        raise SystemExit("torchrl_b200 needs a CUDA device (there is no CPU path)")
-    device = torch.device("cuda:{}".format(args.device))
-    env = get_vec_env(params["env_name"], params["env"], args.vec_env_nums, device=device)
-    eval_env = get_vec_env(params["env_name"], params["env"], args.vec_env_nums, device=device)
-    env.seed(args.seed)
-    torch.manual_seed(args.seed)
-    np.random.seed(args.seed)
-    random.seed(args.seed)
-    torch.cuda.manual_seed_all(args.seed)
-
-    experiment_name = os.path.split(os.path.splitext(args.config)[0])[-1] if args.id is None else args.id
-    logger = Logger(experiment_name, params['env_name'], args.seed, params, args.log_dir, args.overwrite)
-    general = dict(params['general_setting'])
-    buffer_param = params['replay_buffer']
-    replay_buffer = BaseReplayBuffer(env_nums=args.vec_env_nums, max_replay_buffer_size=int(buffer_param['size']),
-                                     time_limit_filter=buffer_param['time_limit_filter'])
-    net = dict(params['net'], base_type=networks.MLPBase, activation_func=torch.nn.ReLU)
-    o, a = env.observation_space.shape[0], env.action_space.shape[0]
-    pf = policies.GuassianContPolicy(input_shape=o, output_shape=2 * a, **net, **params['policy'])
-    qf1 = networks.QNet(input_shape=o + a, output_shape=1, **net)
-    qf2 = networks.QNet(input_shape=o + a, output_shape=1, **net)
-    collector = VecCollector(env=env, pf=pf, eval_env=eval_env, replay_buffer=replay_buffer, device=device,
-                             train_render=False, **params["collector"])
-    general.update(env=env, replay_buffer=replay_buffer, logger=logger, device=device, collector=collector,
-                   save_dir=osp.join(logger.work_dir, "model"))
-    agent = TwinSACQ(pf=pf, qf1=qf1, qf2=qf2, **params["twin_sac_q"], **general)
-    agent.train()
+def experiment(run):
+    cfg = run.params
+    trunk = dict(cfg["net"], base_type=networks.MLPBase, activation_func=torch.nn.ReLU)
+    o, a = run.obs_dim, run.act_dim
+    pf = policies.GuassianContPolicy(input_shape=o, output_shape=2 * a, **trunk, **cfg["policy"])
+    critics = [networks.QNet(input_shape=o + a, output_shape=1, **trunk) for _ in range(2)]
+    ring = BaseReplayBuffer(**run.buffer_kwargs())
+    collector = VecCollector(**run.collector_kwargs(pf, ring))
+    TwinSACQ(pf=pf, qf1=critics[0], qf2=critics[1], **cfg["twin_sac_q"], **run.agent_kwargs(ring, collector)).train()
 
 
 if __name__ == "__main__":
-    _args = get_args()
-    experiment(_args, get_params(_args.config))
+    main(experiment)

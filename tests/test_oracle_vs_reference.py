@@ -269,3 +269,219 @@ def test_logger_files_match_reference(tmp_path, capsys):
     assert out["mine"][0] == out["ref"][0]
     assert out["mine"][1] == out["ref"][1]
     assert out["ref"][0].count("\n") == 4 and "Training/policy_loss_Std" in out["ref"][0]
+
+
+def test_networks_and_policies_are_state_dict_compatible_with_reference():
+    """networks/{init,base,nets}.py, policies/continuous_policy.py: equal seeds give bit-identical parameters
+    (same creation order and RNG consumption), identical state_dict keys / shapes (so `model_*.pth` snapshots load
+    into either code base, algo/rl_algo.py:90-94) and identical CPU forward outputs."""
+    import torch
+    import torch.nn as nn
+    from oracle import reference_loader
+    reference_loader.load()
+    import torchrl.networks as rnet
+    import torchrl.policies as rpol
+    import torchrl_b200.networks as mnet
+    import torchrl_b200.policies as mpol
+
+    def build(net_mod, pol_mod, seed):
+        torch.manual_seed(seed)
+        kw = dict(hidden_shapes=[32, 24], append_hidden_shapes=[], base_type=net_mod.MLPBase, activation_func=nn.Tanh)
+        kw2 = dict(hidden_shapes=[32], append_hidden_shapes=[16], base_type=net_mod.MLPBase, activation_func=nn.ReLU)
+        cnn = dict(hidden_shapes=[[16, [8, 8], [4, 4], [0, 0]], [32, [4, 4], [2, 2], [0, 0]]], append_hidden_shapes=[64],
+                   base_type=net_mod.CNNBase, activation_func=nn.ReLU)
+        return [
+            ("Net", net_mod.Net(input_shape=17, output_shape=1, **kw)),
+            ("Net+append", net_mod.Net(input_shape=17, output_shape=3, **kw2)),
+            ("QNet", net_mod.QNet(input_shape=23, output_shape=1, **kw)),
+            ("BasicBias", pol_mod.GuassianContPolicyBasicBias(input_shape=17, output_shape=6, tanh_action=True, **kw)),
+            ("Gaussian", pol_mod.GuassianContPolicy(input_shape=17, output_shape=12, tanh_action=True, **kw)),
+            ("FixGaussian", pol_mod.FixGuassianContPolicy(input_shape=17, output_shape=6, norm_std_explore=0.1,
+                                                        tanh_action=True, **kw)),
+            ("Det", pol_mod.DetContPolicy(input_shape=17, output_shape=6, tanh_action=True, **kw)),
+            ("CNN", net_mod.Net(input_shape=(4, 84, 84), output_shape=6, **cnn)),
+        ]
+
+    ref, mine = build(rnet, rpol, 7), build(mnet, mpol, 7)
+    x = torch.randn(5, 17)
+    for (name, a), (_, b) in zip(ref, mine):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys()), name
+        for k in sa:
+            assert torch.equal(sa[k], sb[k]), (name, k)
+        b.load_state_dict(sa)                                  # a reference snapshot loads into the product net
+        with torch.no_grad():
+            if name == "QNet":
+                ya, yb = a([x, torch.randn(5, 6).fill_(0.3)]), b([x, torch.randn(5, 6).fill_(0.3)])
+            elif name == "CNN":
+                img = torch.rand(2, 4, 84, 84)
+                ya, yb = a(img), b(img)
+            else:
+                ya, yb = a(x), b(x)
+        ya = ya if isinstance(ya, (tuple, list)) else [ya]
+        yb = yb if isinstance(yb, (tuple, list)) else [yb]
+        for u, v in zip(ya, yb):
+            assert torch.equal(u, v), name
+
+
+def test_train_loop_bookkeeping_matches_reference(tmp_path):
+    """RLAlgo.train (algo/rl_algo.py:96-165): with the same stub collector / logger the product's epoch loop makes the
+    same calls in the same order -- epoch rows (keys, key order, values), evaluation cadence, best / periodic /
+    final snapshots, running-average windows -- as the reference's."""
+    import torch
+    from oracle import reference_loader
+    reference_loader.load()
+    import gym                                  # the oracle's stand-in (oracle/shims), on sys.path after load()
+    from torchrl.algo.rl_algo import RLAlgo as RefAlgo
+    from torchrl_b200.algo.rl_algo import RLAlgo
+
+    class Col:
+        epoch_frames = 64
+
+        def __init__(self):
+            self.k = self.e = 0
+            self.terminated = False
+
+        def train_one_epoch(self):
+            self.k += 1
+            return {"train_rewards": [float(self.k * 10 + i) for i in range(self.k % 3)],
+                    "train_epoch_reward": 1.5 * self.k}
+
+        def eval_one_epoch(self):
+            self.e += 1
+            return {"eval_rewards": [(-1.0) ** self.e * 2.0 * self.e, float(self.e)], "eval_traj_length": 100.0 + self.e}
+
+        def terminate(self):
+            self.terminated = True
+
+    class Log:
+        def __init__(self):
+            self.rows, self.finished = [], False
+
+        def add_epoch_info(self, epoch, frames, seconds, infos, csv_write=True):
+            self.rows.append((epoch, frames, list(infos.keys()),
+                              {k: float(v) for k, v in infos.items() if "Time" not in k}))
+
+        def add_update_info(self, info):
+            pass
+
+        def finish(self):
+            self.finished = True
+
+    class Env:
+        action_space = gym.spaces.Box(-np.ones(3), np.ones(3))
+        _obs_normalizer = None
+
+    def instrument(cls):
+        class Agent(cls):
+            def snapshot(self, prefix, epoch):
+                self.snaps.append(epoch)
+
+            def update_per_epoch(self):
+                self.updates += 1
+
+            def finish_epoch(self):
+                return {"extra/epoch": float(self.current_epoch)}
+
+            def _device_sync(self):
+                pass
+        return Agent
+
+    col_r, log_r = Col(), Log()
+    ref = instrument(RefAlgo)(env=Env(), replay_buffer=None, collector=col_r, logger=log_r, num_epochs=7,
+                              batch_size=64, device="cpu", save_interval=3, eval_interval=2, save_dir=str(tmp_path / "r"))
+    ref.snaps, ref.updates = [], 0
+    ref.train()
+
+    col_m, log_m = Col(), Log()
+    mine = object.__new__(instrument(RLAlgo))
+    mine.device = torch.device("cpu")
+    mine._init_bookkeeping(Env(), None, col_m, log_m, None, 0.99, 7, 64, 3, 2, str(tmp_path / "m"))
+    mine.snaps, mine.updates = [], 0
+    mine.train()
+
+    assert mine.snaps == ref.snaps and mine.updates == ref.updates == 7
+    assert col_m.terminated and log_m.finished and col_m.e == col_r.e
+    assert len(log_m.rows) == len(log_r.rows) == 4
+    for (e0, f0, k0, v0), (e1, f1, k1, v1) in zip(log_r.rows, log_m.rows):
+        assert (e0, f0, k0) == (e1, f1, k1)
+        for k in v0:
+            assert v0[k] == v1[k] or (np.isnan(v0[k]) and np.isnan(v1[k])), k
+    assert list(mine.episode_rewards) == list(ref.episode_rewards)
+    assert list(mine.training_episode_rewards) == list(ref.training_episode_rewards)
+    assert mine.best_eval == ref.best_eval
+
+
+@pytest.mark.parametrize("argv", [[], ["--seed", "3", "--vec_env_nums", "16", "--config", "c.json", "--id", "x", "--overwrite"],
+                                  ["--no_cuda", "--device", "2", "--save_dir", "/tmp/s", "--log_dir", "/tmp/l",
+                                   "--proc_nums", "8", "--eval_worker_nums", "1"]])
+def test_command_line_flags_match_reference(argv, monkeypatch):
+    """utils/args.py:6-46: same flags, types and defaults (the example scripts read the namespace)."""
+    import sys
+    from oracle import reference_loader
+    reference_loader.load()
+    from torchrl.utils.args import get_args as ref_get_args
+    from torchrl_b200.utils.args import get_args
+    monkeypatch.setattr(sys, "argv", ["prog"] + argv)
+    assert vars(ref_get_args()) == vars(get_args(argv))
+
+
+def test_algo_utils_match_reference():
+    """algo/utils.py:5-32: huber, quantile_regression_loss, Polyak / hard target updates and the linear LR
+    schedule give bit-identical results."""
+    import copy
+    import torch
+    from oracle import reference_loader
+    reference_loader.load()
+    import torchrl.algo.utils as ref
+    import torchrl_b200.algo.utils as mine
+    torch.manual_seed(0)
+    x = torch.randn(64) * 2
+    assert torch.equal(ref.huber(x), mine.huber(x)) and torch.equal(ref.huber(x, 0.3), mine.huber(x, 0.3))
+    for dt in (torch.float32, torch.float64):
+        tau = ((2 * torch.arange(9) + 1) / 18.0).to(dt)
+        s, t = torch.randn(5, 9, dtype=dt), torch.randn(5, 9, dtype=dt)
+        assert torch.equal(ref.quantile_regression_loss(tau, s, t), mine.quantile_regression_loss(tau, s, t))
+    src = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    tgt_a = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+    tgt_b = copy.deepcopy(tgt_a)
+    for _ in range(3):
+        ref.soft_update_from_to(src, tgt_a, 0.005)
+        mine.soft_update_from_to(src, tgt_b, 0.005)
+    for p, q in zip(tgt_a.parameters(), tgt_b.parameters()):
+        assert torch.equal(p, q)
+    ref.copy_model_params_from_to(src, tgt_a)
+    mine.copy_model_params_from_to(src, tgt_b)
+    for p, q, r in zip(tgt_a.parameters(), tgt_b.parameters(), src.parameters()):
+        assert torch.equal(p, q) and torch.equal(q, r)
+    oa, ob = torch.optim.Adam(tgt_a.parameters(), lr=1.0), torch.optim.Adam(tgt_b.parameters(), lr=1.0)
+    for epoch in (0, 17, 487):
+        ref.update_linear_schedule(oa, epoch, 488, 3e-4)
+        mine.update_linear_schedule(ob, epoch, 488, 3e-4)
+        assert oa.param_groups[0]["lr"] == ob.param_groups[0]["lr"]
+
+
+def test_epsilon_greedy_policy_matches_reference():
+    """policies/discrete_policies.py:25-74: same exploration schedule and, with the reference's NumPy noise stream,
+    the same decisions."""
+    import torch
+    from oracle import reference_loader
+    reference_loader.load()
+    import torchrl.policies as rpol
+    import torchrl_b200.policies as mpol
+    torch.manual_seed(0)
+    qf = torch.nn.Linear(5, 4)
+    kw = dict(qf=qf, start_epsilon=1.0, end_epsilon=0.1, decay_frames=20, action_shape=4)
+    ref, mine = rpol.EpsilonGreedyDQNDiscretePolicy(**kw), mpol.EpsilonGreedyDQNDiscretePolicy(**kw)
+    obs = torch.randn(30, 1, 5)
+    mpol.set_noise_mode("reference_cpu")
+    try:
+        np.random.seed(3)
+        a_ref = [(ref.explore(o)["action"].clone(), ref.epsilon) for o in obs]
+        np.random.seed(3)
+        a_mine = [(mine.explore(o)["action"].clone(), mine.epsilon) for o in obs]
+    finally:
+        mpol.set_noise_mode("philox")
+    for (a0, e0), (a1, e1) in zip(a_ref, a_mine):
+        assert e0 == e1 and torch.equal(a0, a1)
+    assert mine.count == ref.count == 30 and mine.epsilon == 0.1

@@ -30,31 +30,33 @@ class A2C(OnRLAlgo):
         self.entropy_coeff = entropy_coeff
         self.vf_criterion = torch.nn.MSELoss()
 
+    def _minibatch(self, batch, keys):
+        return [torch.as_tensor(batch[k], dtype=torch.float32, device=self.device) for k in keys]
+
+    @staticmethod
+    def _four_stats(prefix, t):
+        return {prefix + '/mean': t.mean().item(), prefix + '/std': t.std().item(),
+                prefix + '/max': t.max().item(), prefix + '/min': t.min().item()}
+
     def update(self, batch):
-        """One A2C minibatch update (a2c.py:45-112); torch autograd for the losses (cold path),
-        fused clip+Adam for the step."""
+        """One A2C minibatch update (a2c.py:45-112): policy-gradient loss with normalised advantages and an
+        entropy bonus, MSE critic; torch autograd for the two losses (cold path; PPO is the tuned agent), fused
+        clip(0.5)+Adam for both networks in one step."""
         self.training_update_num += 1
-        dev = self.device
-        obs = torch.as_tensor(batch['obs'], dtype=torch.float32, device=dev)
-        acts = torch.as_tensor(batch['acts'], dtype=torch.float32, device=dev)
-        advs = torch.as_tensor(batch['advs'], dtype=torch.float32, device=dev)
-        est_rets = torch.as_tensor(batch['estimate_returns'], dtype=torch.float32, device=dev)
-        out = self.pf.update(obs, acts)
-        log_probs, ent = out['log_prob'], out['ent']
+        obs, acts, advs, est_rets = self._minibatch(batch, ('obs', 'acts', 'advs', 'estimate_returns'))
+        dist_out = self.pf.update(obs, acts)
+        log_probs, ent = dist_out['log_prob'], dist_out['ent']
         advs = (advs - advs.mean()) / (advs.std() + 1e-5)
-        assert log_probs.shape == advs.shape
-        policy_loss = (-log_probs * advs).mean() - self.entropy_coeff * ent.mean()
+        assert log_probs.shape == advs.shape, (log_probs.shape, advs.shape)
+        policy_loss = -(log_probs * advs).mean() - self.entropy_coeff * ent.mean()
         values = self.vf(obs)
         vf_loss = self.vf_criterion(values, est_rets)
         (policy_loss + vf_loss).backward()      # disjoint parameter sets: same grads as two backward calls
         self.opt.step()
-        info = {'Training/policy_loss': policy_loss.item(), 'Training/vf_loss': vf_loss.item(),
-                'v_pred/mean': values.mean().item(), 'v_pred/std': values.std().item(),
-                'v_pred/max': values.max().item(), 'v_pred/min': values.min().item()}
-        if 'std' in out:
-            std = out['std']
-            info.update({'std/mean': std.mean().item(), 'std/std': std.std().item(),
-                         'std/max': std.max().item(), 'std/min': std.min().item()})
+        info = {'Training/policy_loss': policy_loss.item(), 'Training/vf_loss': vf_loss.item()}
+        info.update(self._four_stats('v_pred', values))
+        if 'std' in dist_out:
+            info.update(self._four_stats('std', dist_out['std']))
         info['ent'] = ent.mean().item()
         info['log_prob'] = log_probs.mean().item()
         return info

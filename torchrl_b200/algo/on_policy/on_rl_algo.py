@@ -1,25 +1,31 @@
-"""On-policy base: GAE over the epoch's rollout, then minibatch updates
+"""On-policy base: bootstrap the value of the state after the last stored row, turn the epoch's rollout into
+advantages / returns on the device (K6), then hand minibatches of whole time-rows to `update`
 (API of /root/reference/torchrl/algo/on_policy/on_rl_algo.py:6-48)."""
 import torch
 
 from ..rl_algo import RLAlgo
 
+_KEYS = ("obs", "acts", "advs", "estimate_returns")
+
 
 class OnRLAlgo(RLAlgo):
     def __init__(self, shuffle=True, tau=None, gae=True, **kwargs):
         super().__init__(**kwargs)
-        self.sample_key = ["obs", "acts", "advs", "estimate_returns"]
-        self.shuffle = shuffle
-        self.tau = tau
-        self.gae = gae
+        self.shuffle, self.tau, self.gae = shuffle, tau, gae
+        self.sample_key = list(_KEYS)
+
+    def _bootstrap_value(self):
+        """V(next_obs[T-1]) * (1 - terminals[T-1]) as a contiguous (N,) device vector (on_rl_algo.py:23-27); no
+        host copy."""
+        tail = self.replay_buffer.last_sample(['next_obs', 'terminals', 'time_limits'])
+        alive = 1.0 - tail['terminals'].reshape(-1).float()
+        with torch.no_grad():
+            return (self.vf(tail['next_obs']).reshape(-1) * alive).contiguous()
 
     def process_epoch_samples(self):
-        """last_value = V(next_obs[T-1]) * (1 - terminals[T-1]); then GAE or discounted returns
-        (on_rl_algo.py:22-33).  All on the device, no host copy."""
-        sample = self.replay_buffer.last_sample(['next_obs', 'terminals', 'time_limits'])
-        with torch.no_grad():
-            last_value = self.vf(sample['next_obs']).reshape(-1)
-            last_value = (last_value * (1.0 - sample['terminals'].reshape(-1).float())).contiguous()
+        """Fill `_advs` / `_estimate_returns` of the buffer: GAE(lambda = tau) or plain discounted returns
+        (on_rl_algo.py:28-33)."""
+        last_value = self._bootstrap_value()
         if self.gae:
             self.replay_buffer.generalized_advantage_estimation(last_value, self.discount, self.tau)
         else:
@@ -27,9 +33,9 @@ class OnRLAlgo(RLAlgo):
 
     def update_per_epoch(self):
         self.process_epoch_samples()
+        record = self.logger.add_update_info
         for batch in self.replay_buffer.one_iteration(self.batch_size, self.sample_key, self.shuffle):
-            infos = self.update(batch)
-            self.logger.add_update_info(infos)
+            record(self.update(batch))
 
     @property
     def networks(self):

@@ -41,41 +41,69 @@ class SegmentOptimizer:
         self.flat.step(active_mask=1 << self.seg)
 
 
+class _Stopwatch:
+    """Accumulates wall time per phase between two epoch reports."""
+
+    def __init__(self):
+        self.spent = {}
+
+    def add(self, phase, seconds):
+        self.spent[phase] = self.spent.get(phase, 0.0) + seconds
+
+    def take(self, phase):
+        return self.spent.pop(phase, 0)
+
+
 class RLAlgo:
+    """Owns the epoch loop: collect -> update -> (every eval_interval) evaluate + report -> (every save_interval)
+    snapshot.  Subclasses provide `update_per_epoch`, the network lists and optionally pretrain / start_epoch /
+    finish_epoch hooks."""
+
     def __init__(self, env=None, replay_buffer=None, collector=None, logger=None, grad_clip=None, discount=0.99,
                  num_epochs=3000, batch_size=128, device='cpu', save_interval=100, eval_interval=1, save_dir=None,
                  use_cuda_graph=True, dist=None, resume_checkpoints=False):
-        self.env = env
-        self.continuous = is_box(self.env.action_space)
-        self.replay_buffer = replay_buffer
-        self.collector = collector
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("torchrl_b200 agents run on a CUDA device (there is no CPU path); got %r" % (device,))
-        self.discount = discount
-        self.num_epochs = num_epochs
-        self.epoch_frames = self.collector.epoch_frames
-        self.batch_size = batch_size
-        self.training_update_num = 0
-        self.sample_key = None
-        self.grad_clip = grad_clip
-        self.logger = logger
-        self.episode_rewards = deque(maxlen=30)
-        self.training_episode_rewards = deque(maxlen=30)
-        self.save_interval = save_interval
-        self.save_dir = save_dir
-        if self.save_dir is not None:
-            pathlib.Path(self.save_dir).mkdir(parents=True, exist_ok=True)
-        self.best_eval = None
-        self.eval_interval = eval_interval
-        self.explore_time = 0
-        self.train_time = 0
-        self.start = time.time()
+        self._init_bookkeeping(env, replay_buffer, collector, logger, grad_clip, discount, num_epochs, batch_size,
+                               save_interval, eval_interval, save_dir)
         self.use_cuda_graph = bool(use_cuda_graph)
         self.dist = dist                    # None or a torchrl_b200.distributed.DataParallelContext
+        self.resume_checkpoints = bool(resume_checkpoints)
+
+    def _init_bookkeeping(self, env, replay_buffer, collector, logger, grad_clip, discount, num_epochs, batch_size,
+                          save_interval, eval_interval, save_dir):
+        """Everything the epoch loop needs that does not touch the device."""
+        self.env, self.replay_buffer, self.collector, self.logger = env, replay_buffer, collector, logger
+        self.continuous = is_box(env.action_space)
+        self.discount, self.grad_clip = discount, grad_clip
+        self.num_epochs, self.batch_size = num_epochs, batch_size
+        self.epoch_frames = collector.epoch_frames
+        self.training_update_num = 0
+        self.sample_key = None
+        self.episode_rewards = deque(maxlen=30)              # evaluation returns (running average)
+        self.training_episode_rewards = deque(maxlen=30)     # finished training episodes
+        self.save_interval, self.eval_interval = save_interval, eval_interval
+        self.save_dir = save_dir
+        if save_dir is not None:
+            pathlib.Path(save_dir).mkdir(parents=True, exist_ok=True)
+        self.best_eval = None
+        self._watch = _Stopwatch()
+        self.start = time.time()
         self.current_epoch = 0
         self.first_epoch = 0                # load_checkpoint moves it past the last finished epoch
-        self.resume_checkpoints = bool(resume_checkpoints)
+        self.use_cuda_graph = True
+        self.dist = None
+        self.resume_checkpoints = False
+
+    # the two phase timers of the reference, kept as attributes for code that reads them
+    @property
+    def explore_time(self):
+        return self._watch.spent.get("explore", 0)
+
+    @property
+    def train_time(self):
+        return self._watch.spent.get("train", 0)
 
     # ------------------------------------------------------------------ resume (absent in the reference)
     def save_checkpoint(self, path):
@@ -90,6 +118,7 @@ class RLAlgo:
         self.first_epoch = load_checkpoint(self, path) + 1
         return self.first_epoch
 
+    # ------------------------------------------------------------------ hooks
     def start_epoch(self):
         pass
 
@@ -102,71 +131,75 @@ class RLAlgo:
     def update_per_epoch(self):
         pass
 
+    def _device_sync(self):
+        torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------ snapshots
     def snapshot(self, prefix, epoch):
         """model_{name}_{epoch}.pth state_dicts + pickled obs normaliser (rl_algo.py:83-94)."""
         if prefix is None:
             return
-        if hasattr(self.env, "_obs_normalizer") and self.env._obs_normalizer is not None:
+        normalizer = getattr(self.env, "_obs_normalizer", None)
+        if normalizer is not None:
             with open(osp.join(prefix, "_obs_normalizer_{}.pkl".format(epoch)), "wb") as f:
-                pickle.dump(self.env._obs_normalizer, f)
+                pickle.dump(normalizer, f)
         for name, network in self.snapshot_networks:
             torch.save(network.state_dict(), osp.join(prefix, "model_{}_{}.pth".format(name, epoch)))
 
+    # ------------------------------------------------------------------ the loop
+    def _collect_and_update(self):
+        """One epoch of data + learning; returns the collector's summary."""
+        t0 = time.time()
+        summary = self.collector.train_one_epoch()
+        self.training_episode_rewards.extend(summary["train_rewards"])
+        t1 = time.time()
+        self._watch.add("explore", t1 - t0)
+        self.update_per_epoch()
+        self._device_sync()
+        self._watch.add("train", time.time() - t1)
+        return summary
+
+    def _evaluate_and_report(self, epoch, total_frames, summary, extra):
+        """Evaluation episodes, best-model snapshot and the epoch row of the log (rl_algo.py:125-157)."""
+        t0 = time.time()
+        evals = self.collector.eval_one_epoch()
+        eval_time = time.time() - t0
+        returns = evals.pop("eval_rewards")
+        self.episode_rewards.extend(returns)
+        score = np.mean(returns)
+        if self.best_eval is None or score > self.best_eval:
+            self.best_eval = score
+            self.snapshot(self.save_dir, 'best')
+        trained = self.training_episode_rewards
+        row = {
+            "Running_Average_Rewards": np.mean(self.episode_rewards),
+            "Train_Epoch_Reward": summary["train_epoch_reward"],
+            "Running_Training_Average_Rewards": np.mean(trained) if len(trained) else float("nan"),
+            "Explore_Time": self._watch.take("explore"),
+            "Train___Time": self._watch.take("train"),
+            "Eval____Time": eval_time,
+        }
+        row.update(evals)
+        row.update(extra)
+        self.logger.add_epoch_info(epoch, total_frames, time.time() - self.start, row)
+        self.start = time.time()
+
     def train(self):
         self.pretrain()
-        total_frames = 0
-        if hasattr(self, "pretrain_frames"):
-            total_frames = self.pretrain_frames
+        total_frames = getattr(self, "pretrain_frames", 0)
         self.start_epoch()
         for epoch in range(self.first_epoch, self.num_epochs):
             self.current_epoch = epoch
             self.start_epoch()
-
-            t0 = time.time()
-            training_epoch_info = self.collector.train_one_epoch()
-            for reward in training_epoch_info["train_rewards"]:
-                self.training_episode_rewards.append(reward)
-            self.explore_time += time.time() - t0
-
-            t0 = time.time()
-            self.update_per_epoch()
-            torch.cuda.synchronize(self.device)
-            self.train_time += time.time() - t0
-
-            finish_epoch_info = self.finish_epoch()
+            summary = self._collect_and_update()
+            extra = self.finish_epoch()
             total_frames += self.epoch_frames
-
             if epoch % self.eval_interval == 0:
-                t0 = time.time()
-                eval_infos = self.collector.eval_one_epoch()
-                eval_time = time.time() - t0
-                infos = {}
-                for reward in eval_infos["eval_rewards"]:
-                    self.episode_rewards.append(reward)
-                mean_eval = np.mean(eval_infos["eval_rewards"])
-                if self.best_eval is None or mean_eval > self.best_eval:
-                    self.best_eval = mean_eval
-                    self.snapshot(self.save_dir, 'best')
-                del eval_infos["eval_rewards"]
-                infos["Running_Average_Rewards"] = np.mean(self.episode_rewards)
-                infos["Train_Epoch_Reward"] = training_epoch_info["train_epoch_reward"]
-                infos["Running_Training_Average_Rewards"] = \
-                    np.mean(self.training_episode_rewards) if len(self.training_episode_rewards) else float("nan")
-                infos["Explore_Time"] = self.explore_time
-                infos["Train___Time"] = self.train_time
-                infos["Eval____Time"] = eval_time
-                self.explore_time = 0
-                self.train_time = 0
-                infos.update(eval_infos)
-                infos.update(finish_epoch_info)
-                self.logger.add_epoch_info(epoch, total_frames, time.time() - self.start, infos)
-                self.start = time.time()
-
+                self._evaluate_and_report(epoch, total_frames, summary, extra)
             if epoch % self.save_interval == 0:
                 self.snapshot(self.save_dir, epoch)
                 if self.resume_checkpoints and self.save_dir is not None:
                     self.save_checkpoint(osp.join(self.save_dir, "checkpoint_latest.pt"))
-
         self.snapshot(self.save_dir, "finish")
         self.collector.terminate()
         self.logger.finish()

@@ -27,49 +27,54 @@ class UniformPolicyDiscrete(nn.Module):
         return {"action": np.random.randint(self.action_num)}
 
 
+def linear_decay(start, end, frames, count):
+    """Exploration rate after `count` decisions: linear from `start` to `end` over `frames`, then flat
+    (discrete_policies.py:44-49)."""
+    if count >= frames:
+        return end
+    return start - (start - end) * (count / frames)
+
+
+def _uniform_and_random_actions(shape, n_actions, device):
+    """(u in [0,1), a in {0..n_actions-1}) per decision.  "reference_cpu" mode draws them from the global NumPy
+    stream in the reference's order (rand, then randint); otherwise they are generated on the device."""
+    if D.get_noise_mode() == "reference_cpu":
+        u = torch.Tensor(np.random.rand(*shape)).to(device)
+        a = torch.LongTensor(np.random.randint(low=0, high=n_actions, size=shape)).to(device)
+        return u, a
+    return torch.rand(shape, device=device), torch.randint(0, n_actions, shape, device=device)
+
+
 class EpsilonGreedyDQNDiscretePolicy:
-    """epsilon-greedy wrapper over a Q network (discrete_policies.py:25-74)."""
+    """epsilon-greedy decisions on top of a Q network (discrete_policies.py:25-74).  Not an nn.Module, like in the
+    reference: `to` / `parameters` forward to the wrapped network."""
 
     def __init__(self, qf, start_epsilon, end_epsilon, decay_frames, action_shape):
         self.qf = qf
-        self.start_epsilon = start_epsilon
-        self.end_epsilon = end_epsilon
-        self.decay_frames = decay_frames
-        self.count = 0
+        self.start_epsilon, self.end_epsilon, self.decay_frames = start_epsilon, end_epsilon, decay_frames
         self.action_shape = action_shape
-        self.epsilon = self.start_epsilon
+        self.count = 0
+        self.epsilon = start_epsilon
         self.continuous = False
 
     def q_to_a(self, q):
         return q.max(dim=-1, keepdim=True)[1].detach()
 
-    def _anneal(self):
-        self.count += 1
-        if self.count < self.decay_frames:
-            self.epsilon = self.start_epsilon - (self.start_epsilon - self.end_epsilon) * (self.count / self.decay_frames)
-        else:
-            self.epsilon = self.end_epsilon
-
     def tick(self):
-        """Advance the epsilon schedule by one step (host).  Collectors that replay a captured step graph call
-        this outside the graph and pass the value through a device scalar (`explore(x, epsilon=tensor)`)."""
-        self._anneal()
+        """Advance the schedule by one decision (host side).  Collectors that replay a captured step graph call
+        this outside the graph and hand the rate over in a device scalar (`explore(x, epsilon=tensor)`)."""
+        self.count += 1
+        self.epsilon = linear_decay(self.start_epsilon, self.end_epsilon, self.decay_frames, self.count)
 
     def explore(self, x, epsilon=None):
         if epsilon is None:
-            self._anneal()
+            self.tick()
             epsilon = self.epsilon
         x = x.squeeze(0)
         output = self.qf(x)
-        action = self.q_to_a(output)
-        if D.get_noise_mode() == "reference_cpu":
-            r = torch.Tensor(np.random.rand(*action.shape)).to(x.device)
-            random_action = torch.LongTensor(np.random.randint(low=0, high=self.action_shape, size=action.shape)).to(x.device)
-        else:
-            r = torch.rand(action.shape, device=x.device)
-            random_action = torch.randint(0, self.action_shape, action.shape, device=x.device)
-        action = torch.where(r < epsilon, random_action, action)
-        return {"q_value": output, "action": action}
+        greedy = self.q_to_a(output)
+        u, random_action = _uniform_and_random_actions(tuple(greedy.shape), self.action_shape, x.device)
+        return {"q_value": output, "action": torch.where(u < epsilon, random_action, greedy)}
 
     def eval_act(self, x):
         with torch.no_grad():

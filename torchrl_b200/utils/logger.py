@@ -28,46 +28,59 @@ except ImportError:
     wandb = None
 
 
-class Logger:
-    def __init__(self, experiment_id, env_name, seed, params, log_dir="./log", overwrite=False, quiet=False):
-        self.logger = logging.getLogger("{}_{}_{}".format(experiment_id, env_name, str(seed)))
-        self.logger.handlers = []
-        self.logger.propagate = False
-        sh = logging.StreamHandler(sys.stdout)
-        sh.setFormatter(logging.Formatter("%(asctime)s %(threadName)s %(levelname)s: %(message)s"))
-        sh.setLevel(logging.INFO)
-        self.logger.addHandler(sh)
-        self.logger.setLevel(logging.WARNING if quiet else logging.INFO)
-        self.quiet = quiet
+_AGGREGATES = (("Mean", np.mean), ("Std", np.std), ("Max", np.max), ("Min", np.min))
 
-        work_dir = os.path.join(log_dir, experiment_id, env_name, str(seed))
-        self.work_dir = work_dir
-        if os.path.exists(work_dir):
+
+def _console_logger(name, quiet):
+    log = logging.getLogger(name)
+    log.handlers = []
+    log.propagate = False
+    handler = logging.StreamHandler(sys.stdout)
+    handler.setFormatter(logging.Formatter("%(asctime)s %(threadName)s %(levelname)s: %(message)s"))
+    handler.setLevel(logging.INFO)
+    log.addHandler(handler)
+    log.setLevel(logging.WARNING if quiet else logging.INFO)
+    return log
+
+
+def _git_revision():
+    try:
+        import git
+        return git.Repo(search_parent_directories=True).head.object.hexsha
+    except Exception:
+        return "unknown"
+
+
+class Logger:
+    """Run directory `log_dir/experiment_id/env_name/seed` holding params.json, git_hash.txt and log.csv; per-update
+    scalars are buffered by `add_update_info` and folded into Mean / Std / Max / Min columns by the next
+    `add_epoch_info`, which also appends the epoch's row (values printed with 5 decimals)."""
+
+    def __init__(self, experiment_id, env_name, seed, params, log_dir="./log", overwrite=False, quiet=False):
+        run = "{}_{}_{}".format(experiment_id, env_name, str(seed))
+        self.logger = _console_logger(run, quiet)
+        self.quiet = quiet
+        self.work_dir = os.path.join(log_dir, experiment_id, env_name, str(seed))
+        if os.path.exists(self.work_dir):
             assert overwrite, "Experiment Exists and Did not set overwrite"
-            shutil.rmtree(work_dir)
-        os.makedirs(work_dir, exist_ok=True)
-        self.tf_writer = tensorboardX.SummaryWriter(work_dir) if tensorboardX is not None else None
-        self.csv_file_path = os.path.join(work_dir, 'log.csv')
-        self.git_file_path = os.path.join(work_dir, 'git_hash.txt')
-        try:
-            import git
-            sha = git.Repo(search_parent_directories=True).head.object.hexsha
-        except Exception:
-            sha = "unknown"
+            shutil.rmtree(self.work_dir)
+        os.makedirs(self.work_dir, exist_ok=True)
+        self.tf_writer = tensorboardX.SummaryWriter(self.work_dir) if tensorboardX is not None else None
+        self.csv_file_path = os.path.join(self.work_dir, 'log.csv')
+        self.git_file_path = os.path.join(self.work_dir, 'git_hash.txt')
         with open(self.git_file_path, 'w') as f:
-            f.write(sha)
+            f.write(_git_revision())
         self.update_count = 0
         self.stored_infos = {}
-        serialisable = {k: v for k, v in params.items() if _jsonable(v)}
-        with open(os.path.join(work_dir, 'params.json'), 'w') as f:
-            json.dump(serialisable, f, indent=2)
+        config = {k: v for k, v in params.items() if _jsonable(v)}
+        with open(os.path.join(self.work_dir, 'params.json'), 'w') as f:
+            json.dump(config, f, indent=2)
         self.logger.info("Experiment Name:{}".format(experiment_id))
-        self.logger.info(json.dumps(serialisable, indent=2))
+        self.logger.info(json.dumps(config, indent=2))
         params["name_combine"] = "{}_{}".format(experiment_id, env_name)
         self.use_wb = wandb is not None and 'project' in params
         if self.use_wb:
-            wandb.init(project=params['project'], name="{}_{}_{}".format(experiment_id, env_name, str(seed)),
-                       group="{}_{}".format(experiment_id, env_name), config=serialisable)
+            wandb.init(project=params['project'], name=run, group=params["name_combine"], config=config)
 
     def finish(self):
         if self.use_wb:
@@ -77,59 +90,51 @@ class Logger:
         self.logger.info(info)
 
     def add_update_info(self, infos):
-        for k, v in infos.items():
-            self.stored_infos.setdefault(k, []).append(v)
+        for key, value in infos.items():
+            self.stored_infos.setdefault(key, []).append(value)
         self.update_count += 1
 
+    def _columns(self, infos):
+        """(name, value) pairs of one epoch row after the three fixed columns: the epoch scalars in the order
+        given, then Mean / Std / Max / Min of every buffered per-update scalar."""
+        for key, value in infos.items():
+            yield key, value
+        for key, values in self.stored_infos.items():
+            for suffix, fold in _AGGREGATES:
+                yield "{}_{}".format(key, suffix), fold(values)
+
     def add_epoch_info(self, epoch_num, total_frames, total_time, infos, csv_write=True):
-        if csv_write:
-            csv_titles = ["EPOCH", "Time Consumed", "Total Frames"] if epoch_num == 0 else None
-            csv_values = [epoch_num, total_time, total_frames]
-        self.logger.info("EPOCH:{}".format(epoch_num))
-        self.logger.info("Time Consumed:{}s".format(total_time))
-        self.logger.info("Total Frames:{}s".format(total_frames))
-        table = [["Name", "Value"]]
-        wb = {"EPOCH": epoch_num, "Time Consumed": total_time, "Total Frames": total_frames}
-        for k, v in infos.items():
-            if self.tf_writer is not None:
-                self.tf_writer.add_scalar(k, v, total_frames)
-            table.append([k, "{:.5f}".format(v)])
-            if csv_write:
-                if csv_titles is not None:
-                    csv_titles.append(k)
-                csv_values.append("{:.5f}".format(v))
-            wb[k] = v
-        table.append([])
-        names, methods = ["Mean", "Std", "Max", "Min"], [np.mean, np.std, np.max, np.min]
-        table.append(["Name"] + names)
-        for k, vals in self.stored_infos.items():
-            row = [k]
-            for name, method in zip(names, methods):
-                val = method(vals)
-                if self.tf_writer is not None:
-                    self.tf_writer.add_scalar("{}_{}".format(k, name), val, total_frames)
-                row.append("{:.5f}".format(val))
-                if csv_write:
-                    if csv_titles is not None:
-                        csv_titles.append("{}_{}".format(k, name))
-                    csv_values.append("{:.5f}".format(val))
-                wb["{}_{}".format(k, name)] = val
-            table.append(row)
+        fixed = [("EPOCH", epoch_num), ("Time Consumed", total_time), ("Total Frames", total_frames)]
+        for label, value in fixed:
+            self.logger.info("{}:{}{}".format(label, value, "" if label == "EPOCH" else "s"))
+        columns = list(self._columns(infos))
+        if self.tf_writer is not None:
+            for name, value in columns:
+                self.tf_writer.add_scalar(name, value, total_frames)
         if self.use_wb:
-            wandb.log(wb)
-        self.stored_infos = {}
+            wandb.log(dict(fixed + columns))
         if csv_write:
             with open(self.csv_file_path, 'a') as f:
-                w = csv.writer(f)
-                if csv_titles is not None:
-                    w.writerow(csv_titles)
-                w.writerow(csv_values)
+                writer = csv.writer(f)
+                if epoch_num == 0:
+                    writer.writerow([label for label, _ in fixed] + [name for name, _ in columns])
+                writer.writerow([value for _, value in fixed] + ["{:.5f}".format(value) for _, value in columns])
         if not self.quiet:
-            if tabulate is not None:
-                print(tabulate(table))
-            else:
-                for r in table:
-                    print(*r)
+            self._print_table(infos, columns[len(infos):])
+        self.stored_infos = {}
+
+    def _print_table(self, infos, aggregated):
+        table = [["Name", "Value"]] + [[k, "{:.5f}".format(v)] for k, v in infos.items()] + [[]]
+        table.append(["Name"] + [suffix for suffix, _ in _AGGREGATES])
+        for i in range(0, len(aggregated), len(_AGGREGATES)):
+            group = aggregated[i:i + len(_AGGREGATES)]
+            key = group[0][0][:-len("_" + _AGGREGATES[0][0])]
+            table.append([key] + ["{:.5f}".format(v) for _, v in group])
+        if tabulate is not None:
+            print(tabulate(table))
+        else:
+            for row in table:
+                print(*row)
 
 
 class NullLogger:
