@@ -26,6 +26,7 @@
 // order by splitk_reduce_kernel (deterministic).
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace trl {
 
@@ -122,6 +123,11 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
 }
 
+__device__ __forceinline__ float tanh_mufu(float x) {      // 1 - 2 / (exp(2x) + 1), same as csrc/skinny.cu
+  x = fminf(fmaxf(x, -15.f), 15.f);
+  return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+}
+
 struct GemmParams {
   const float* __restrict__ bias;  // (256) added in the epilogue, or nullptr
   int act;                         // 0 none, 1 tanh, 2 relu (applied after the bias)
@@ -133,7 +139,10 @@ struct GemmParams {
 
 // MN == false: C = A . B^T with A (M x K), B (256 x K) row-major (K-major operands).
 // MN == true : C = A^T . B  with A (K x M), B (K x 256) row-major (M/N-major operands; the wgrad shape).
-template <bool MN>
+// STAGED (opt-in, TORCHRL_B200_GEMM_STAGED=1; not yet validated on hardware): the epilogue goes through shared
+// memory so that every global store instruction of a warp writes 512 contiguous bytes instead of 16 bytes of 32
+// different rows, and tanh uses two MUFU ops (|abs err| < 2e-7) instead of libdevice tanhf on only four warps.
+template <bool MN, bool STAGED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const GemmParams p) {
@@ -264,6 +273,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int quad = warp & 3;
     const long long row = static_cast<long long>(m_blk) * kBM + quad * 32 + lane;
     float* crow = p.C + (static_cast<long long>(split) * p.M + row) * p.ldc;
+    // STAGED: the operand stages are free now (tmem_full fires after the last MMA has read them): this warp's 32
+    // rows are parked there with a pitch of 260 floats (conflict-free 16-byte accesses by row AND by column)
+    constexpr int kPitch = kBN + 4;
+    float* park = reinterpret_cast<float*>(smem) + static_cast<size_t>(quad) * 32 * kPitch;
 #pragma unroll 1
     for (int c = 0; c < kBN / 32; ++c) {
       uint32_t r[32];
@@ -278,8 +291,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < p.M) {
-        float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+      if (STAGED || row < p.M) {
+        float4* dst = STAGED ? reinterpret_cast<float4*>(park + lane * kPitch + c * 32)
+                             : reinterpret_cast<float4*>(crow + c * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -287,11 +301,28 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (p.bias) {   // fused Linear epilogue: z + b, then the activation (same op order as bias_act_fwd_kernel)
             const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * j);
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            if (p.act == 1) { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
-            else if (p.act == 2) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (p.act == 1) {
+              if (STAGED) { v.x = tanh_mufu(v.x); v.y = tanh_mufu(v.y); v.z = tanh_mufu(v.z); v.w = tanh_mufu(v.w); }
+              else { v.x = tanhf(v.x); v.y = tanhf(v.y); v.z = tanhf(v.z); v.w = tanhf(v.w); }
+            } else if (p.act == 2) {
+              v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            }
           }
           dst[j] = v;
         }
+      }
+    }
+    if (STAGED) {
+      __syncwarp();                                     // the 32 rows of this warp are complete in shared memory
+      const long long row0 = static_cast<long long>(m_blk) * kBM + quad * 32;
+      float* cbase = p.C + (static_cast<long long>(split) * p.M + row0) * p.ldc;
+#pragma unroll 4
+      for (int rr = 0; rr < 32; ++rr) {
+        if (row0 + rr >= p.M) break;
+        const float4* src = reinterpret_cast<const float4*>(park + rr * kPitch);
+        float4* out = reinterpret_cast<float4*>(cbase + static_cast<long long>(rr) * p.ldc);
+        out[lane] = src[lane];                          // 512 contiguous bytes per warp instruction
+        out[lane + 32] = src[lane + 32];
       }
     }
   }
@@ -362,6 +393,14 @@ static PFN_encodeTiled get_encode() {
 }
 
 // rows x K fp32 row-major matrix, box = (32 contiguous elements, box_rows), 128B swizzle
+static bool staged_epilogue() {
+  static const bool on = [] {
+    const char* e = getenv("TORCHRL_B200_GEMM_STAGED");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
 static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_t K, uint32_t box_rows,
                      CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_encodeTiled enc = get_encode();
@@ -400,14 +439,17 @@ TRL_API int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   GemmParams p{bias, act, splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
   const dim3 grid(static_cast<unsigned>(ceil_div<long long>(M, kBM)), static_cast<unsigned>(splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gemm_tf32x3_kernel<false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  if (staged_epilogue()) gemm_tf32x3_kernel<false, true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  else gemm_tf32x3_kernel<false, false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
   int rc = check_launch("gemm_tf32x3_kernel<nt>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
@@ -436,14 +478,17 @@ TRL_API int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t
   }
   static bool attr_set = false;
   if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     attr_set = true;
   }
   GemmParams p{nullptr, 0, splits > 1 ? workspace : C, M, static_cast<int>(K / kBK / splits), kBN};
   const dim3 grid(static_cast<unsigned>(M / kBM), static_cast<unsigned>(splits));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gemm_tf32x3_kernel<true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  if (staged_epilogue()) gemm_tf32x3_kernel<true, true><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
+  else gemm_tf32x3_kernel<true, false><<<grid, kGemmThreads, kSmemBytes, st>>>(map_a, map_b, p);
   int rc = check_launch("gemm_tf32x3_kernel<tn>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
