@@ -485,3 +485,47 @@ def test_epsilon_greedy_policy_matches_reference():
     for (a0, e0), (a1, e1) in zip(a_ref, a_mine):
         assert e0 == e1 and torch.equal(a0, a1)
     assert mine.count == ref.count == 30 and mine.epsilon == 0.1
+
+
+@pytest.mark.parametrize("adt", [np.float32, np.float64])
+def test_host_vecenv_and_wrapper_chain_match_reference(adt):
+    """env/vecenv.py:6-78 + get_env.py:52-67 (NormAct, RewardShift, TimeLimitAugment): the product's host VecEnv over
+    its one-object wrapper chain returns the same observations / rewards / flags, step for step, as the reference's
+    VecEnv over the reference's stacked gym wrappers (same action dtype handed through)."""
+    from oracle import reference_loader, synth_env
+    reference_loader.load()
+    from torchrl.env.get_env import get_single_env as ref_single
+    from torchrl.env.vecenv import VecEnv as RefVecEnv
+    from torchrl_b200.hostenv import VecEnv, get_single_env
+    N, T = 5, 14
+    param = {"reward_scale": 0.25}
+    ref = RefVecEnv(N, ref_single, ["SynthHalfCheetah-v0", dict(param)])
+    mine = VecEnv(N, get_single_env, ["SynthHalfCheetah-v0", dict(param), synth_env.make_env])
+
+    def shorten(env):                     # reach the TimeLimit core of either wrapper chain
+        core = env
+        while not hasattr(core, "_max_episode_steps") or hasattr(core, "env") and hasattr(core.env, "_max_episode_steps"):
+            core = core.env
+        core._max_episode_steps = 6
+    for e in ref.envs:
+        shorten(e)
+    for e in mine.envs:
+        shorten(e)
+    ref.seed(9)
+    mine.seed(9)
+    np.testing.assert_array_equal(ref.reset(), mine.reset())
+    rs = np.random.RandomState(1)
+    for t in range(T):
+        acts = rs.uniform(-1.4, 1.4, size=(N, 6)).astype(adt)
+        o0, r0, d0, i0 = ref.step(acts)
+        o1, r1, d1, i1 = mine.step(acts)
+        np.testing.assert_array_equal(o0, o1)
+        np.testing.assert_array_equal(r0, r1)
+        np.testing.assert_array_equal(d0, d1)
+        np.testing.assert_array_equal(np.asarray(i0["time_limit"]), i1["time_limit"])
+        if d0.any():
+            np.testing.assert_array_equal(ref.partial_reset(d0.squeeze(-1)), mine.partial_reset(d1.squeeze(-1)))
+        if t == 8:
+            ref.eval()
+            mine.eval()                    # RewardShift is train-only
+    assert d0.dtype == d1.dtype and r0.shape == r1.shape == (N, 1)
