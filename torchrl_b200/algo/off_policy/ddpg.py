@@ -60,7 +60,7 @@ class DDPG(OffRLAlgo):
         q_pred = self.qf([obs, acts])
         g, _, _ = ops.twin_mse_loss(q_pred.reshape(-1), None, y, sc, info=info[4:6])
         torch.autograd.backward([q_pred], [g.reshape(q_pred.shape)], inputs=self.opt.segments[1])
-        self.opt.step(active_mask=0b11)
+        self._step(active_mask=0b11)
         self._update_target_networks()
         ops.vec_stats(new_actions.detach().reshape(-1), out=info[10:14])
         if self._explicit_batch is None:

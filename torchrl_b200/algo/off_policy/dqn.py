@@ -71,7 +71,7 @@ class DQN(OffRLAlgo):
                                   weights=None if weights is None else weights.reshape(-1).contiguous(),
                                   td_out=self._td)
         torch.autograd.backward([pred], [grad])
-        self.opt.step()
+        self._step()
         self._update_target_networks()
         if self._explicit_batch is None:
             self._finish_update()

@@ -67,6 +67,28 @@ class OffRLAlgo(RLAlgo):
         """Key of the update-graph variant for the current update (e.g. TD3's delayed actor step)."""
         return 0
 
+    # ------------------------------------------------------------------ data parallel (SURVEY.md 8(e))
+    @property
+    def _dp(self):
+        return self.dist is not None and self.dist.active
+
+    def _step(self, active_mask=None):
+        """Optimizer step of the flat buffer.  Data parallel (ring sharded by env, every rank draws the same row
+        indices from the same host seed): the flat gradient is summed over ranks first and scaled by 1/G inside
+        the Adam kernel, before clipping -- what a single process over all envs would apply.  NOT yet exercised on
+        more than one GPU (the single-process path is unchanged)."""
+        scale = self.dist.all_reduce_grads(self.opt.grad) if self._dp else 1.0
+        self.opt.step(active_mask=active_mask, grad_scale=scale)
+
+    def _all_ranks(self, vec):
+        """Concatenation of a per-rank (B,) vector over ranks (rank order), identical on every rank."""
+        if not self._dp:
+            return vec
+        import torch.distributed as tdist
+        out = torch.empty(vec.numel() * self.dist.world_size, dtype=vec.dtype, device=vec.device)
+        tdist.all_gather_into_tensor(out, vec.contiguous())
+        return out
+
     def _update_body(self, variant):
         raise NotImplementedError
 

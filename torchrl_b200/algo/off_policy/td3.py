@@ -79,14 +79,14 @@ class TD3(OffRLAlgo):
         g1, g2, _ = ops.twin_mse_loss(q1_pred.reshape(-1), q2_pred.reshape(-1), y, sc, info=info[4:6])
         torch.autograd.backward([q1_pred, q2_pred], [g1.reshape(q1_pred.shape), g2.reshape(q2_pred.shape)],
                                 inputs=self.opt.segments[1] + self.opt.segments[2])
-        self.opt.step(active_mask=0b110)
+        self._step(active_mask=0b110)
         if variant == 1:
             new_actions = self.pf(obs)
             q_new = self.qf1([obs, new_actions])            # uses qf1 AFTER its step, like the reference
             info[6:7].copy_((-q_new.detach().mean()).reshape(1))
             seed = torch.full_like(q_new, -1.0 / q_new.numel())
             torch.autograd.backward([q_new], [seed], inputs=self.opt.segments[0])
-            self.opt.step(active_mask=0b001)
+            self._step(active_mask=0b001)
             self._update_target_networks()
             ops.vec_stats(new_actions.detach().reshape(-1), out=info[10:14])
         if self._explicit_batch is None:

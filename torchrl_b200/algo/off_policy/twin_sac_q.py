@@ -91,8 +91,11 @@ class TwinSACQ(OffRLAlgo):
         q2_pred = self.qf2([obs, acts])
         log_alpha = None
         if self.automatic_entropy_tuning:
-            ops.sac_alpha_step(log_probs.detach().reshape(-1), self.target_entropy, self.log_alpha, self._alpha_state,
-                               self.plr, sc, info=info[1:3])
+            lp_all = self._all_ranks(log_probs.detach().reshape(-1))      # temperature sees every rank's samples
+            if lp_all.numel() != sc.B and getattr(self, "_alpha_sc", None) is None:
+                self._alpha_sc = ops.OffPolicyScratch(lp_all.numel(), lp_all.device)
+            ops.sac_alpha_step(lp_all, self.target_entropy, self.log_alpha, self._alpha_state, self.plr,
+                               sc if lp_all.numel() == sc.B else self._alpha_sc, info=info[1:3])
             log_alpha = self.log_alpha
         with torch.no_grad():
             t_actions, t_logp, _, _ = self._sample(next_obs, False)
@@ -121,7 +124,7 @@ class TwinSACQ(OffRLAlgo):
         torch.autograd.backward(roots, seeds, inputs=pf_params)
         torch.autograd.backward([q1_pred, q2_pred], [g1.reshape(q1_pred.shape), g2.reshape(q2_pred.shape)],
                                 inputs=self.opt.segments[1] + self.opt.segments[2])
-        self.opt.step()
+        self._step()
         self._update_target_networks()
         if self._explicit_batch is None:
             self._finish_update()

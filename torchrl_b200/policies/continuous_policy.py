@@ -6,6 +6,7 @@ entropy are produced by the CUDA library in one launch (csrc/collect.cu) and not
 copied to the host inside ``explore``.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -29,7 +30,9 @@ class _DeviceRng:
 
     def ensure(self, device):
         if self.counter is None or self.counter.device != torch.device(device):
-            self.seed = int(torch.initial_seed()) & ((1 << 63) - 1)
+            # one stream per rank: shards of a data-parallel job must not explore with identical noise
+            rank = int(os.environ.get("RANK", "0"))
+            self.seed = (int(torch.initial_seed()) + 0x9E3779B97F4A7C15 * rank) & ((1 << 63) - 1)
             self.counter = torch.zeros(1, dtype=torch.int64, device=device)
         return self
 
