@@ -92,10 +92,13 @@ class TwinSACQ(OffRLAlgo):
         log_alpha = None
         if self.automatic_entropy_tuning:
             lp_all = self._all_ranks(log_probs.detach().reshape(-1))      # temperature sees every rank's samples
-            if lp_all.numel() != sc.B and getattr(self, "_alpha_sc", None) is None:
-                self._alpha_sc = ops.OffPolicyScratch(lp_all.numel(), lp_all.device)
-            ops.sac_alpha_step(lp_all, self.target_entropy, self.log_alpha, self._alpha_state, self.plr,
-                               sc if lp_all.numel() == sc.B else self._alpha_sc, info=info[1:3])
+            alpha_sc = sc
+            if lp_all.numel() != sc.B:                  # more samples than the per-rank scratch was sized for
+                alpha_sc = getattr(self, "_alpha_sc", None)
+                if alpha_sc is None or alpha_sc.B != lp_all.numel():
+                    alpha_sc = self._alpha_sc = ops.OffPolicyScratch(lp_all.numel(), lp_all.device)
+            ops.sac_alpha_step(lp_all, self.target_entropy, self.log_alpha, self._alpha_state, self.plr, alpha_sc,
+                               info=info[1:3])
             log_alpha = self.log_alpha
         with torch.no_grad():
             t_actions, t_logp, _, _ = self._sample(next_obs, False)
