@@ -137,8 +137,11 @@ int trl_grad_sumsq(const float* grad, const int64_t* seg_begin_host, int nseg, u
 int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int64_t* seg_begin_host,
                   int nseg, unsigned active_mask, const double* sumsq3, const float* lr_dev,
                   const float* max_norm_host, const float* eps_host, float beta1, float beta2,
-                  float grad_scale, int zero_grad, void* stream);
-int trl_polyak_update(float* target, const float* source, int64_t n, float tau, void* stream);
+                  float grad_scale, int zero_grad, float* param_hi, float* param_lo, void* stream);
+/* param_hi / param_lo, target_hi / target_lo (both or neither): TF32 planes hi = tf32(w), lo = w - hi of the
+ * updated weights, kept current for trl_gemm3_pair's pre-split B operand. */
+int trl_polyak_update(float* target, const float* source, int64_t n, float tau, float* target_hi,
+                      float* target_lo, void* stream);
 
 /* ---- K10: off-policy TD targets and loss reductions.
  * TwinSACQ.update (algo/off_policy/twin_sac_q.py:84-219), TD3.update (algo/off_policy/td3.py:57-154),
@@ -199,6 +202,17 @@ int trl_gemm_tf32x3_nt(const float* A, const float* B, float* C, int64_t M, int6
 int trl_gemm_tf32x3_tn(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
                        float* workspace, void* stream);
 int trl_transpose_f32(const float* in, float* out, int64_t rows, int cols, void* stream);
+/* The same three shapes on CTA PAIRS (tcgen05 cta_group::2, csrc/gemm_pair.cu): one MMA covers 256 x 256, each
+ * CTA stages half of B, 3-stage ring, coalesced epilogue.  C (M x 256) = act(A (M x K) . B + bias):
+ * b_nmajor == 0: B is (256 x K) row-major (Linear forward, networks/base.py:24-44: x W^T + b);
+ * b_nmajor != 0: B is (K x 256) row-major (the dgrad shape g W, no transpose of the weights).
+ * b_lo != NULL: (b_hi, b_lo) are pre-split TF32 planes of B (trl_split_tf32 / trl_adam_step / trl_polyak_update);
+ * b_lo == NULL: b_hi is the raw fp32 matrix, split in shared memory.  Any M >= 1, K % 32 == 0. */
+int trl_gemm3_pair(const float* A, const float* b_hi, const float* b_lo, float* C, int64_t M, int64_t K,
+                   int b_nmajor, const float* bias, int act, void* stream);
+/* C (M x 256) = A (K x M)^T . B (K x 256), M % 256 == 0, deterministic split-K (the weight-gradient shape). */
+int trl_gemm3_pair_tn(const float* A, const float* B, float* C, int64_t M, int64_t K, int splits,
+                      float* workspace, void* stream);
 
 /* ---- "skinny" Linear layers of the small MLPs (first layer K = obs_dim, output layer N = act_dim / 1;
  * networks/base.py:24-44, networks/nets.py:13-52): memory-bound fp32 kernels, bias / activation fused. */

@@ -53,8 +53,8 @@ SIGNATURES = {
     "trl_gaussian_log_prob": [vp, vp, i32, vp, i64, i32, i32, vp, vp],
     "trl_grad_sumsq_blocks": [i32],
     "trl_grad_sumsq": [vp, vp, i32, u32, vp, vp, f64, f64, vp, vp, vp],
-    "trl_adam_step": [vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp, f32, f32, f32, i32, vp],
-    "trl_polyak_update": [vp, vp, i64, f32, vp],
+    "trl_adam_step": [vp, vp, vp, vp, vp, i32, u32, vp, vp, vp, vp, f32, f32, f32, i32, vp, vp, vp],
+    "trl_polyak_update": [vp, vp, i64, f32, vp, vp, vp],
     "trl_bias_act_bwd_scratch_floats": [i64, i32],
     "trl_bias_act_fwd": [vp, vp, i64, i32, i32, vp],
     "trl_split_tf32": [vp, i64, vp, vp, vp],
@@ -65,6 +65,8 @@ SIGNATURES = {
     "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp, i32, vp],
     "trl_gemm_tf32x3_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_transpose_f32": [vp, vp, i64, i32, vp],
+    "trl_gemm3_pair": [vp, vp, vp, vp, i64, i64, i32, vp, i32, vp],
+    "trl_gemm3_pair_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_skinny_k_fwd": [vp, vp, vp, vp, i64, i32, i32, i32, vp],
     "trl_skinny_tn_scratch_floats": [i64, i32, i32],
     "trl_skinny_tn": [vp, vp, vp, vp, i64, i32, i32, i32, vp, vp],

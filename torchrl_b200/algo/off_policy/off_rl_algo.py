@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from ... import ops
+from ...networks import fused
 from ..rl_algo import RLAlgo
 
 
@@ -139,6 +140,7 @@ class OffRLAlgo(RLAlgo):
                 for info in infos:
                     self.logger.add_update_info(info)
 
+    @fused.presplit_scope
     def update_per_epoch(self, flush_infos=True):
         """opt_times x {random_batch; update} (off_rl_algo.py:46-51)."""
         ub = self._ub or self._ub_setup()
@@ -159,6 +161,7 @@ class OffRLAlgo(RLAlgo):
             for info in self._last_infos:
                 self.logger.add_update_info(info)
 
+    @fused.presplit_scope
     def update(self, batch):
         """Eager single update on an explicit batch dict (reference signature); syncs to return floats."""
         dev = self.device

@@ -165,14 +165,17 @@ class PPO(A2C):
             for i, k in enumerate(_ADV_KEYS):
                 info[k] = float(row[20 + i])
             info['Training/vf_loss'] = float(row[16])
-            info['grad_norm/vf'] = float(np.sqrt(log64[u][1]))
+            # the flat gradient holds the SUM over ranks; the averaged gradient's norm is what one process sees
+            gs = 1.0 / self.dist.world_size if (self.dist is not None and self.dist.active) else 1.0
+            info['grad_norm/vf'] = float(np.sqrt(log64[u][1])) * gs
             for i, k in enumerate(_INFO_KEYS_ACTOR):
                 info[k] = float(row[i])
-            info['grad_norm/pf'] = float(np.sqrt(log64[u][0]))
+            info['grad_norm/pf'] = float(np.sqrt(log64[u][0])) * gs
             infos.append(info)
         return infos
 
     # ------------------------------------------------------------------ reference API
+    @fused.presplit_scope
     def update_per_epoch(self, flush_infos=True):
         """ppo.py:27-39: GAE, linear LR decay, target <- pf, opt_epochs passes of minibatches.
         flush_infos=False skips the end-of-epoch read-back of the logged scalars (benchmarking the
@@ -180,7 +183,7 @@ class PPO(A2C):
         self.process_epoch_samples()
         atu.update_linear_schedule(self.pf_optimizer, self.current_epoch, self.num_epochs, self.plr)
         atu.update_linear_schedule(self.vf_optimizer, self.current_epoch, self.num_epochs, self.vlr)
-        self._target_flat.data.copy_(self.opt.seg_slice(0))      # copy_model_params_from_to(pf, target_pf)
+        self._target_flat.copy_from(self.opt.seg_slice(0))       # copy_model_params_from_to(pf, target_pf)
         self._cache_old_logp()
         st = self._mb_state or self._mb_setup()
         st["upd"].zero_()
@@ -201,6 +204,7 @@ class PPO(A2C):
             for info in self._last_infos:
                 self.logger.add_update_info(info)
 
+    @fused.presplit_scope
     def update(self, batch):
         """Eager single-minibatch update with the reference's signature (ppo.py:124-152): `batch`
         holds (B,D) arrays for obs, acts, advs, estimate_returns, values; returns the info dict of
@@ -235,7 +239,7 @@ class PPO(A2C):
             scale = self.dist.all_reduce_grads(self.opt.grad)
         self.opt.step(grad_scale=scale)
         row = info32.cpu().numpy()
-        norms = self.opt.grad_norms().cpu().numpy()
+        norms = self.opt.grad_norms().cpu().numpy() * scale
         info = {k: float(row[20 + i]) for i, k in enumerate(_ADV_KEYS)}
         info['Training/vf_loss'] = float(row[16])
         info['grad_norm/vf'] = float(norms[1])

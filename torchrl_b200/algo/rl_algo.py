@@ -185,8 +185,14 @@ class RLAlgo:
         self.start = time.time()
 
     def train(self):
-        self.pretrain()
-        total_frames = getattr(self, "pretrain_frames", 0)
+        if self.first_epoch == 0:
+            self.pretrain()
+            total_frames = getattr(self, "pretrain_frames", 0)
+        else:
+            # resumed through load_checkpoint: the pretraining data is already in the restored ring and the
+            # frame count continues where the interrupted run stopped
+            total_frames = getattr(self, "total_frames",
+                                   getattr(self, "pretrain_frames", 0) + self.first_epoch * self.epoch_frames)
         self.start_epoch()
         for epoch in range(self.first_epoch, self.num_epochs):
             self.current_epoch = epoch
@@ -194,6 +200,7 @@ class RLAlgo:
             summary = self._collect_and_update()
             extra = self.finish_epoch()
             total_frames += self.epoch_frames
+            self.total_frames = total_frames
             if epoch % self.eval_interval == 0:
                 self._evaluate_and_report(epoch, total_frames, summary, extra)
             if epoch % self.save_interval == 0:
@@ -212,11 +219,12 @@ class RLAlgo:
         captured inside the update graph.  The periodic HARD copy (rl_algo.py:173-176) depends on a
         host counter, so it is applied by `_maybe_hard_update` outside of any captured graph."""
         if self.use_soft_update:
-            ops.polyak_update(self._target_flat.data, self._target_source(), self.tau)
+            ops.polyak_update(self._target_flat.data, self._target_source(), self.tau,
+                              planes=(self._target_flat.hi, self._target_flat.lo))
 
     def _maybe_hard_update(self):
         if not self.use_soft_update and self.training_update_num % self.target_hard_update_period == 0:
-            self._target_flat.data.copy_(self._target_source())
+            self._target_flat.copy_from(self._target_source())
 
     @property
     def networks(self):

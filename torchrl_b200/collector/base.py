@@ -13,6 +13,7 @@ import torch
 
 from .. import _lib, ops
 from ..env import synth_spec
+from ..networks import fused
 from ..policies import distribution as D
 from ..spaces import is_box
 
@@ -225,6 +226,7 @@ class VecCollector:
             g.replay()                      # capture does not execute: run the step now
         self._host_after_step()
 
+    @fused.presplit_scope
     def take_actions(self):
         """One env step for all envs; returns the summed (un-bootstrapped) reward of the step."""
         before = self._epoch_reward.sum()
@@ -255,6 +257,7 @@ class VecCollector:
         self.train_epoch_reward = float(self._epoch_reward.sum().item())
         return {'train_rewards': self.train_rews, 'train_epoch_reward': self.train_epoch_reward}
 
+    @fused.presplit_scope
     def rollout_no_sync(self):
         """The T collector steps of one epoch with no host read-back at all (what train_one_epoch
         runs before fetching its summary)."""
@@ -265,6 +268,7 @@ class VecCollector:
         for _ in range(self.sample_epoch_frames):
             self._step()
 
+    @fused.presplit_scope
     def eval_one_epoch(self):
         """Deterministic-policy evaluation episodes on the eval env (collector/base.py:232-280)."""
         eval_env = self.eval_env

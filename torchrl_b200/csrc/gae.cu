@@ -130,12 +130,14 @@ __global__ void __launch_bounds__(1024) gae_chunked_kernel(const GaeParams p) {
       }
     }
     {
-      const long long tn = t0 + TC;  // first step of the next chunk (>= 1 always)
+      // first step of the next chunk; in the ragged head super-chunk (T % span != 0) whole chunks lie at t < 0 and
+      // tn can be <= 0: those steps are identities, nothing is read for them (vn stays 0)
+      const long long tn = t0 + TC;
 #pragma unroll
       for (int i = 0; i < VEC; ++i) vn[i] = 0.f;
       if (env_ok) {
-        if (tn < T) load_f<VEC>(p.values + tn * N + env0, vn);
-        else load_f<VEC>(p.last_value + env0, vn);
+        if (tn >= T) load_f<VEC>(p.last_value + env0, vn);
+        else if (tn >= 0) load_f<VEC>(p.values + tn * N + env0, vn);
       }
     }
     // ---- pass 1: per-step coefficients, chunk composition --------------------------

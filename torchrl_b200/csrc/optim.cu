@@ -99,7 +99,17 @@ struct AdamParams {
   unsigned active_mask;
   int zero_grad;
   float grad_scale;                   // multiplies g before everything (1/world_size after an all-reduce SUM)
+  float* __restrict__ w_hi;           // optional TF32 planes of the updated weights for csrc/gemm_pair.cu:
+  float* __restrict__ w_lo;           //   hi = tf32(w), lo = w - hi (both NULL: not maintained)
 };
+
+__device__ __forceinline__ void split_tf32_store(float w, float* __restrict__ hi, float* __restrict__ lo, long long i) {
+  unsigned u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(w));
+  const float h = __uint_as_float(u);
+  hi[i] = h;
+  lo[i] = w - h;
+}
 
 __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(const AdamParams p) {
   const long long total = p.seg.begin[p.seg.nseg];
@@ -123,15 +133,21 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(const AdamParams
     p.m[i] = m;
     p.v[i] = v;
     const float denom = sqrtf(v) / bc2_sqrt + p.eps[s];
-    p.w[i] = p.w[i] - (p.lr[s] / bc1) * (m / denom);
+    const float w = p.w[i] - (p.lr[s] / bc1) * (m / denom);
+    p.w[i] = w;
+    if (p.w_hi) split_tf32_store(w, p.w_hi, p.w_lo, i);
     if (p.zero_grad) p.g[i] = 0.f;
   }
 }
 
-__global__ void polyak_kernel(float* __restrict__ target, const float* __restrict__ source, long long n, float tau) {
+__global__ void polyak_kernel(float* __restrict__ target, const float* __restrict__ source, long long n, float tau,
+                              float* __restrict__ t_hi, float* __restrict__ t_lo) {
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    target[i] = target[i] * (1.0f - tau) + source[i] * tau;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float w = target[i] * (1.0f - tau) + source[i] * tau;
+    target[i] = w;
+    if (t_hi) split_tf32_store(w, t_hi, t_lo, i);
+  }
 }
 
 static bool fill_segs(SegTable& t, const int64_t* seg_begin, int nseg) {
@@ -164,7 +180,7 @@ TRL_API int trl_grad_sumsq(const float* grad, const int64_t* seg_begin_host, int
 
 TRL_API int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, const int64_t* seg_begin_host,
                           int nseg, unsigned active_mask, const double* sumsq3, const float* lr_dev, const float* max_norm_host, const float* eps_host, float beta1,
-                          float beta2, float grad_scale, int zero_grad, void* stream) {
+                          float beta2, float grad_scale, int zero_grad, float* param_hi, float* param_lo, void* stream) {
   using namespace trl;
   AdamParams p;
   TRL_REQUIRE(seg_begin_host && fill_segs(p.seg, seg_begin_host, nseg), "trl_adam_step: bad segment table");
@@ -175,7 +191,9 @@ TRL_API int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_
     p.max_norm[i] = i < nseg ? max_norm_host[i] : 0.f;
     p.eps[i] = i < nseg ? eps_host[i] : 1e-8f;
   }
+  TRL_REQUIRE((param_hi == nullptr) == (param_lo == nullptr), "trl_adam_step: param_hi / param_lo must be given together");
   p.beta1 = beta1; p.beta2 = beta2; p.active_mask = active_mask; p.zero_grad = zero_grad; p.grad_scale = grad_scale;
+  p.w_hi = param_hi; p.w_lo = param_lo;
   const long long total = p.seg.begin[nseg];
   if (total == 0) return TRL_OK;
   long long blocks = ceil_div<long long>(total, kOptThreads);
@@ -184,13 +202,16 @@ TRL_API int trl_adam_step(float* param, float* grad, float* exp_avg, float* exp_
   return check_launch("adam_step_kernel");
 }
 
-TRL_API int trl_polyak_update(float* target, const float* source, int64_t n, float tau, void* stream) {
+TRL_API int trl_polyak_update(float* target, const float* source, int64_t n, float tau, float* target_hi,
+                              float* target_lo, void* stream) {
   using namespace trl;
   TRL_REQUIRE(n >= 0, "trl_polyak_update: negative size");
   if (n == 0) return TRL_OK;
   TRL_REQUIRE(target && source, "trl_polyak_update: null pointer");
+  TRL_REQUIRE((target_hi == nullptr) == (target_lo == nullptr), "trl_polyak_update: target_hi / target_lo must be given together");
   long long blocks = ceil_div<long long>(n, 256);
   if (blocks > 4LL * kNumSM) blocks = 4LL * kNumSM;
-  polyak_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(target, source, n, tau);
+  polyak_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(target, source, n, tau,
+                                                                                          target_hi, target_lo);
   return check_launch("polyak_kernel");
 }

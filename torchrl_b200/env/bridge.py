@@ -87,9 +87,23 @@ class HostEnvBridge:
     def seed(self, seed):
         self.host.seed(seed)
 
+    def _wait_staging(self):
+        """The pinned staging block may still be the source of an H2D copy in flight (launch_step / a previous
+        upload return without waiting): wait for that copy before the host writes into the block again."""
+        ev = getattr(self, "_h2d_done", None)
+        if ev is not None:
+            ev.synchronize()
+
+    def _mark_staging(self):
+        if getattr(self, "_h2d_done", None) is None:
+            self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.device))
+
     def _upload_obs(self, obs):
+        self._wait_staging()
         np.copyto(self._h_obs, np.asarray(obs).reshape(self._h_obs.shape), casting="same_kind")
         self._dev[:self._obs_cut].copy_(self._pin[:self._obs_cut], non_blocking=True)
+        self._mark_staging()
 
     def _observe(self, update):
         """NormObs.observation (/root/reference/torchrl/env/base_wrapper.py:118-121) on the device."""
@@ -122,6 +136,7 @@ class HostEnvBridge:
         else:
             acts = self._act_np.astype(np.int64)
         obs, rew, done, infos = self.host.step(acts)
+        self._wait_staging()
         np.copyto(self._h_obs, np.asarray(obs).reshape(self._h_obs.shape), casting="same_kind")
         np.copyto(self._h_rew, np.asarray(rew).reshape(-1), casting="same_kind")
         done = np.asarray(done).reshape(-1).astype(bool)
@@ -130,6 +145,7 @@ class HostEnvBridge:
         self._h_tl[...] = 0 if tl is None else np.asarray(tl).reshape(-1).astype(bool)
         self.host_done = done
         self._dev.copy_(self._pin, non_blocking=True)
+        self._mark_staging()
         return self._observe(update=True)
 
     def step(self, actions):

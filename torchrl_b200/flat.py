@@ -48,6 +48,33 @@ class FlatParams:
             self.data[o:o + n].copy_(p.data.reshape(-1))
             p.data = self.data[o:o + n].view(p.shape)
         self.params = plist
+        # TF32 planes of every parameter (hi = tf32(w), lo = w - hi) for the pre-split B operand of the CTA-pair
+        # GEMM (csrc/gemm_pair.cu): written by the fused Adam / Polyak kernels, refreshed from `data` on entry
+        # to a `networks.fused.presplit()` scope, looked up by the weight's address inside such a scope only.
+        self.hi = torch.zeros(self.total, dtype=F32, device=self.device)
+        self.lo = torch.zeros(self.total, dtype=F32, device=self.device)
+        if self.device.type == "cuda":
+            from .networks import fused
+            fused.register_flat(self)
+
+    def plane_views(self):
+        """{weight address: (hi, lo)} for the 2-D parameters."""
+        out = {}
+        for p, o in zip(self.params, self.offsets):
+            if p.dim() == 2:
+                n = p.numel()
+                out[p.data_ptr()] = (self.hi[o:o + n].view(p.shape), self.lo[o:o + n].view(p.shape))
+        return out
+
+    def refresh_split(self):
+        """Recompute both planes from `data` (one launch)."""
+        _lib.call("trl_split_tf32", self.data.data_ptr(), self.total, self.hi.data_ptr(), self.lo.data_ptr(),
+                  ops._stream())
+
+    def copy_from(self, src_flat_data):
+        """data <- src (a flat tensor of the same layout); the planes follow."""
+        self.data.copy_(src_flat_data)
+        self.refresh_split()
 
     def seg_slice(self, i, j=None):
         j = i + 1 if j is None else j
@@ -107,7 +134,7 @@ class FlatAdam(FlatParams):
         _lib.call("trl_adam_step", self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
                   self.lr.data_ptr(), self._max_norm_c, self._eps_c, self.betas[0], self.betas[1],
-                  float(grad_scale), int(bool(zero_grad)), st)
+                  float(grad_scale), int(bool(zero_grad)), self.hi.data_ptr(), self.lo.data_ptr(), st)
 
     def grad_norms(self):
         """Pre-clip total norm per segment of the last step (what clip_grad_norm_ returns)."""

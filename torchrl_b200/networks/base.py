@@ -76,7 +76,7 @@ class MLPBase(nn.Module):
 
 
 def head_plain(h, head):
-    if h.is_cuda and h.dtype == torch.float32 and torch.is_grad_enabled():
+    if h.is_cuda and h.dtype == torch.float32:
         return fused.linear_plain(h, head)
     return head(h)
 

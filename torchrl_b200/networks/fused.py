@@ -1,12 +1,19 @@
-"""Linear + activation with the fused CUDA epilogues (csrc/mlp_epilogue.cu).
+"""Linear (+ activation) layers of MLPBase (/root/reference/torchrl/networks/base.py:24-44) on this library's kernels.
 
-The GEMMs stay in cuBLAS (torch.mm); what is fused is everything PyTorch launches *around* them for a
-hidden layer of MLPBase (/root/reference/torchrl/networks/base.py:24-44): bias add + activation in the
-forward (1 launch instead of a cuBLASLt epilogue kernel + an elementwise kernel) and activation-backward +
-bias-gradient reduction in the backward (1 launch instead of an elementwise kernel + a reduce kernel).
-Numerically it is the same fp32 arithmetic in the same order per element (bias added to the GEMM result,
-then the activation); the bias gradient is a fixed-order two-level sum.
+Routing of one Linear layer (default matmul mode "tc3"):
+  * 256 output units, reduction length a multiple of 32, >= _TC3_MIN_ROWS rows: the hand-written tcgen05 3xTF32
+    GEMM on CTA pairs (csrc/gemm_pair.cu; fp32-faithful) -- forward with bias + activation in the TMEM epilogue,
+    dgrad reading the weights N-major (no transpose), wgrad with both operands M/N-major and deterministic split-K.
+    Inside a `presplit()` scope the weights come as pre-split TF32 planes kept current by the fused Adam / Polyak
+    kernels (flat.FlatParams.hi / .lo); elsewhere the kernel splits them in shared memory.
+  * first layer (K = obs_dim <= 24) and output layer (<= 8 units): csrc/skinny.cu (memory-bound fp32 kernels).
+  * anything else: cuBLAS fp32 SIMT + the fused bias/activation epilogues of csrc/mlp_epilogue.cu.
+Numerically every route is fp32 arithmetic (3xTF32: 2e-6 relative at K = 256); the bias gradient is a fixed-order
+two-level sum.
 """
+import os
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -19,17 +26,93 @@ _ENABLED = True
 # "fp32"  : cuBLAS fp32 SIMT sgemm everywhere
 # "tf32x3": error-compensated TF32 through three cuBLAS GEMMs (kept for comparison; no faster than fp32)
 _MATMUL_MODE = "tc3"
-_TC3_MIN_ROWS = 8192
+_TC3_MIN_ROWS = 2048             # one CTA pair per 256 rows: 8 pairs already beat the SIMT sgemm's latency
 _TF32X3_MIN_DIM = 64             # layers narrower than this stay on the plain path
+# "pair": csrc/gemm_pair.cu (cta_group::2, pre-split weights, 3-stage ring) [default]; "single": csrc/gemm_tf32x3.cu
+_GEMM_IMPL = os.environ.get("TORCHRL_B200_GEMM", "pair")
 
 
 def set_matmul_mode(mode):
-    """"fp32" (default) or "tf32x3": x@w computed as x_hi@w_hi + x_lo@w_hi + x_hi@w_lo on the TF32 tensor
-    cores with fp32 accumulation (operands split by csrc/mlp_epilogue.cu:split_tf32_kernel) -- fp32-faithful
-    results (the dropped lo*lo term is O(2^-22)), unlike plain TF32."""
+    """"tc3" (default): 256-wide layers on the tcgen05 3xTF32 kernel, the rest cuBLAS fp32 SIMT; "fp32": cuBLAS
+    fp32 SIMT everywhere; "tf32x3": x@w as x_hi@w_hi + x_lo@w_hi + x_hi@w_lo through three cuBLAS TF32 GEMMs
+    (operands split by csrc/mlp_epilogue.cu:split_tf32_kernel; kept for comparison)."""
     global _MATMUL_MODE
     assert mode in ("fp32", "tf32x3", "tc3")
     _MATMUL_MODE = mode
+
+
+def set_gemm_impl(impl):
+    global _GEMM_IMPL
+    assert impl in ("pair", "single")
+    _GEMM_IMPL = impl
+
+
+# ---- pre-split weight planes ------------------------------------------------------------------------------------
+_FLATS = weakref.WeakSet()       # live flat.FlatParams objects
+_PLANES = {}                     # weight address -> (hi, lo) views into the owning FlatParams' planes
+_PRESPLIT_DEPTH = 0
+
+
+def _drop_planes(ptrs):
+    for q in ptrs:
+        _PLANES.pop(q, None)
+
+
+def register_flat(flat):
+    """Called by flat.FlatParams: remember its TF32 planes per 2-D parameter (dropped when the object dies)."""
+    views = flat.plane_views()
+    _PLANES.update(views)
+    _FLATS.add(flat)
+    weakref.finalize(flat, _drop_planes, list(views.keys()))
+
+
+class presplit:
+    """Scope in which the 256-wide layers read their weights from the pre-split planes.  On entry every live flat
+    parameter buffer refreshes its planes from the current weights (one small launch each); inside the scope the
+    weights may only change through the fused Adam / Polyak kernels or FlatParams.copy_from, which keep the planes
+    current.  Used by the collectors' epochs and the agents' update loops; direct layer calls outside a scope split
+    the weights in shared memory instead (always correct, 32 KB more conversion per stage)."""
+
+    def __enter__(self):
+        global _PRESPLIT_DEPTH
+        if _PRESPLIT_DEPTH == 0 and _MATMUL_MODE == "tc3" and _GEMM_IMPL == "pair":
+            for f in list(_FLATS):
+                f.refresh_split()
+        _PRESPLIT_DEPTH += 1
+        return self
+
+    def __exit__(self, *a):
+        global _PRESPLIT_DEPTH
+        _PRESPLIT_DEPTH -= 1
+
+
+def presplit_scope(fn):
+    """Decorator: run the method inside a `presplit()` scope."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*a, **k):
+        with presplit():
+            return fn(*a, **k)
+    return wrapped
+
+
+def _planes_of(weight):
+    return _PLANES.get(weight.data_ptr()) if _PRESPLIT_DEPTH > 0 else None
+
+
+def mm_fwd(x, weight, bias=None, act=0):
+    """act(x (M,K) @ weight (256,K)^T + bias) on the tensor cores."""
+    if _GEMM_IMPL == "pair":
+        return ops.gemm3_pair(x, weight, planes=_planes_of(weight), bias=bias, act=act)
+    return ops.gemm_tf32x3_nt(x, weight, bias=bias, act=act)
+
+
+def mm_dgrad(gz, weight):
+    """gz (M,256) @ weight (256,256): the weights are read N-major by the pair kernel (no transpose)."""
+    if _GEMM_IMPL == "pair":
+        return ops.gemm3_pair(gz, weight, planes=_planes_of(weight), b_nmajor=True)
+    return ops.gemm_tf32x3_nt(gz, ops.transpose_f32(weight))
 
 
 def get_matmul_mode():
@@ -68,6 +151,8 @@ def wgrad(gz, x, out=None):
         ws = _WGRAD_WS.get(key)
         if ws is None:
             ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
+        if _GEMM_IMPL == "pair" and H % 256 == 0:
+            return ops.gemm3_pair_tn(gz, x, out=out, splits=64, workspace=ws)
         return ops.gemm_tf32x3_tn(gz, x, out=out, splits=64, workspace=ws)
     if (_MATMUL_MODE != "fp32" and K <= 24 and H % 32 == 0 and H <= 256 and _skinny_ok(gz)
             and (out is None or out.is_contiguous())):
@@ -205,7 +290,7 @@ class _LinearAct(torch.autograd.Function):
             return z
         if _tc3_ok(x.shape[0], weight.shape[0], x.shape[1]) and weight.is_contiguous():
             # tcgen05: act(x (M,K) . W (256,K)^T + b), bias + activation fused into the TMEM epilogue
-            z = ops.gemm_tf32x3_nt(x, weight, bias=bias, act=act)
+            z = mm_fwd(x, weight, bias=bias, act=act)
             ctx.save_for_backward(x, weight, z)
             ctx.act, ctx.tc, ctx.params = act, False, (weight, bias)
             return z
@@ -251,7 +336,7 @@ class _LinearAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             if _tc3_ok(M, weight.shape[1], H) and weight.is_contiguous():
-                dx = ops.gemm_tf32x3_nt(gz, ops.transpose_f32(weight))   # gz (M,H) . (W^T) (256,H)^T
+                dx = mm_dgrad(gz, weight)
             else:
                 dx = torch.mm(gz, weight)
         dw = wgrad(gz, x, out=dw_out) if ctx.needs_input_grad[1] else None
@@ -327,7 +412,7 @@ class _MLPTail(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w2, b2, w3, b3, act):
-        y2 = ops.gemm_tf32x3_nt(x, w2, bias=b2, act=act)
+        y2 = mm_fwd(x, w2, bias=b2, act=act)
         M, H = y2.shape
         N = w3.shape[0]
         out = torch.empty(M, N, dtype=torch.float32, device=x.device)
@@ -359,7 +444,7 @@ class _MLPTail(torch.autograd.Function):
                   M, H, N, ctx.act, ws.data_ptr(), ops._stream())
         _lib.add_launches(1)
         dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)      # dW3 (N,H) = g^T y2, db3 = sum g
-        dx = ops.gemm_tf32x3_nt(gz, ops.transpose_f32(w2)) if ctx.needs_input_grad[0] else None
+        dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
         dw2 = wgrad(gz, x, out=dw2_out)
         return (dx, None if dw2_out is not None else dw2, None if db2_out is not None else db2,
                 None if dw3_out is not None else dw3, None if db3_out is not None else db3, None)
@@ -368,7 +453,7 @@ class _MLPTail(torch.autograd.Function):
 def tail_ok(h, fc, act_module, head):
     """True when `head(act(fc(h)))` can run as one _MLPTail node: 256-wide hidden layer on the tcgen05 kernel, an
     output layer of at most 8 units, enough rows, gradients being recorded."""
-    if not (_ENABLED and _SKINNY and h.is_cuda and h.dtype == torch.float32 and torch.is_grad_enabled()):
+    if not (_ENABLED and _SKINNY and h.is_cuda and h.dtype == torch.float32):
         return False
     rows = h.numel() // h.shape[-1]
     return (type(act_module) in ACT_CODES and rows >= max(_TC3_MIN_ROWS, _SKINNY_MIN_ROWS)

@@ -41,8 +41,7 @@ class Net(nn.Module):
         self.seq_append_fcs = nn.Sequential(*self.append_fcs)
 
     def _head(self, h):
-        if (len(self.append_fcs) == 1 and fused.fused_enabled() and h.is_cuda and h.dtype == torch.float32
-                and torch.is_grad_enabled()):
+        if (len(self.append_fcs) == 1 and fused.fused_enabled() and h.is_cuda and h.dtype == torch.float32):
             return fused.linear_plain(h, self.append_fcs[0])
         return self.seq_append_fcs(h)
 

@@ -271,9 +271,12 @@ def gaussian_log_prob(mean, log_std, actions, tanh_action, out=None):
 
 
 # ------------------------------------------------------------------------------------------ K11
-def polyak_update(target_flat, source_flat, tau):
+def polyak_update(target_flat, source_flat, tau, planes=None):
+    """target <- (1 - tau) target + tau source on flat buffers; planes = (hi, lo) flat TF32 planes of the target
+    kept current in the same pass (flat.FlatParams.hi / .lo)."""
+    hi, lo = planes if planes is not None else (None, None)
     _lib.call("trl_polyak_update", _chk(target_flat, F32, "target"), _chk(source_flat, F32, "source"),
-              target_flat.numel(), float(tau), _stream())
+              target_flat.numel(), float(tau), _opt(hi, F32, "hi"), _opt(lo, F32, "lo"), _stream())
 
 
 # ------------------------------------------------------------------------------------------ K10
@@ -424,6 +427,40 @@ def gemm_tf32x3_tn(a, b, out=None, splits=1, workspace=None):
     if splits > 1 and workspace is None:
         workspace = torch.empty(splits * M * 256, dtype=F32, device=a.device)
     _lib.call("trl_gemm_tf32x3_tn", _chk(a, F32, "a"), _chk(b, F32, "b"), _chk(out, F32, "out"), M, K, int(splits),
+              None if workspace is None else workspace.data_ptr(), _stream())
+    if splits > 1:
+        _lib.add_launches(1)
+    return out
+
+
+def gemm3_pair(a, b, out=None, planes=None, b_nmajor=False, bias=None, act=0):
+    """out (M,256) = act(a (M,K) @ B + bias) on CTA pairs (csrc/gemm_pair.cu, tcgen05 cta_group::2, 3xTF32).
+    b_nmajor False: b is (256,K) and B = b^T (Linear forward); True: b is (K,256) and B = b (dgrad).
+    planes = (hi, lo): pre-split TF32 planes of b (same shape), else b is split in shared memory."""
+    M, K = a.shape
+    assert tuple(b.shape) == ((K, 256) if b_nmajor else (256, K)), "B must be (K,256) if b_nmajor else (256,K)"
+    if out is None:
+        out = torch.empty(M, 256, dtype=F32, device=a.device)
+    if planes is not None:
+        hi, lo = planes
+        assert hi.shape == b.shape and lo.shape == b.shape
+        bh, bl = _chk(hi, F32, "b_hi"), _chk(lo, F32, "b_lo")
+    else:
+        bh, bl = _chk(b, F32, "b"), None
+    _lib.call("trl_gemm3_pair", _chk(a, F32, "a"), bh, bl, _chk(out, F32, "out"), M, K, int(bool(b_nmajor)),
+              _opt(bias, F32, "bias"), int(act), _stream())
+    return out
+
+
+def gemm3_pair_tn(a, b, out=None, splits=1, workspace=None):
+    """out (M,256) = a (K,M)^T @ b (K,256) on CTA pairs: the weight-gradient shape, deterministic split-K."""
+    K, M = a.shape
+    assert b.shape == (K, 256), "B must be (K, 256)"
+    if out is None:
+        out = torch.empty(M, 256, dtype=F32, device=a.device)
+    if splits > 1 and workspace is None:
+        workspace = torch.empty(splits * M * 256, dtype=F32, device=a.device)
+    _lib.call("trl_gemm3_pair_tn", _chk(a, F32, "a"), _chk(b, F32, "b"), _chk(out, F32, "out"), M, K, int(splits),
               None if workspace is None else workspace.data_ptr(), _stream())
     if splits > 1:
         _lib.add_launches(1)

@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 FORMAT = 1
-_AGENT_SCALARS = ("current_epoch", "training_update_num", "best_eval", "pretrain_frames")
+_AGENT_SCALARS = ("current_epoch", "training_update_num", "best_eval", "pretrain_frames", "total_frames")
 _COLLECTOR_SCALARS = ("_host_step", "_host_steps")
 _ENV_SCALARS = ("_host_elapsed", "_host_mirror_ok", "training")
 _BUFFER_SCALARS = ("_top", "_size")
@@ -81,11 +81,17 @@ def save_checkpoint(agent, path, include_replay=None):
     return path
 
 
-def _restore(obj, saved, what):
+def _restore(obj, saved, what, device=None):
+    """Copy saved tensors into the live object's tensors IN PLACE.  A saved tensor whose destination does not exist
+    yet (state the object allocates lazily: replay keys, priorities, ...) is materialised with the saved shape on
+    `device`; a destination of another kind is an error -- nothing is dropped silently."""
     for k, v in saved.items():
         dst = getattr(obj, k, None)
+        if dst is None and device is not None:
+            setattr(obj, k, v.to(device, copy=True))
+            continue
         if not torch.is_tensor(dst):
-            continue                                   # lazily created scratch: rebuilt on demand
+            raise ValueError("checkpoint/%s.%s is a tensor but the agent holds %r there" % (what, k, type(dst)))
         if tuple(dst.shape) != tuple(v.shape):
             raise ValueError("checkpoint/%s.%s has shape %s, the agent expects %s -- different configuration"
                              % (what, k, tuple(v.shape), tuple(dst.shape)))
@@ -106,12 +112,18 @@ def load_checkpoint(agent, path):
         for k, v in state["opt"].items():
             getattr(agent.opt, k).copy_(v)
         agent.opt.grad.zero_()
-        _restore(agent, state["agent_tensors"], "agent")
-        _restore(col, state["collector_tensors"], "collector")
-        _restore(env, state["env_tensors"], "env")
+        dev = agent.device
+        _restore(agent, state["agent_tensors"], "agent", dev)
+        _restore(col, state["collector_tensors"], "collector", dev)
+        _restore(env, state["env_tensors"], "env", dev)
         if state["normalizer"] is not None:
-            _restore(env._obs_normalizer, state["normalizer"], "normalizer")
-        _restore(rb, state["buffer_tensors"], "buffer")
+            _restore(env._obs_normalizer, state["normalizer"], "normalizer", dev)
+        if hasattr(rb, "_ensure_prio"):
+            rb._ensure_prio()                          # prioritised ring: priorities exist before they are restored
+        _restore(rb, state["buffer_tensors"], "buffer", dev)
+    for f in (getattr(agent, "opt", None), getattr(agent, "_target_flat", None)):
+        if f is not None and hasattr(f, "refresh_split"):
+            f.refresh_split()                          # TF32 planes follow the restored weights
     for obj, key in ((agent, "agent_scalars"), (col, "collector_scalars"), (env, "env_scalars"),
                      (rb, "buffer_scalars"), (agent.pf, "policy_scalars")):
         for k, v in state[key].items():
