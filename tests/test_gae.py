@@ -80,10 +80,42 @@ def test_gae_kernel_vs_oracle_sizes(T, N):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("T,N", [(128, 4096), (1000, 1024), (3, 128), (64, 128), (65, 384), (129, 256), (191, 37888)])
+def test_gae_tma_kernel_vs_oracle(T, N):
+    """The persistent TMA-staged scan (variant 4, csrc/gae_tma.cu): one tile, several tiles, a ragged earliest tile
+    (T not a multiple of 64: the box starts below row 0), more env groups than SMs -- GAE and discounted returns,
+    filter on and off, against the float64 oracle."""
+    from torchrl_b200 import ops
+    from oracle.make_golden import gae_inputs
+    v, r, t, tl, lv = gae_inputs(T, N, seed=7 * T + N, p_term=0.02, p_tl=0.01)
+    R, V, Tm, TL, LV = _to_dev(v, r, t, tl, lv)
+    for f in (True, False):
+        ea, er = rn.gae(r, v, t, tl, lv, 0.99, 0.95, f)
+        da, dr = rn.discount_return(r, v, t, tl, lv, 0.99, f)
+        a, ret = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, f, variant=4)
+        np.testing.assert_allclose(a.cpu().numpy(), ea, rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(ret.cpu().numpy(), er, rtol=RTOL, atol=ATOL)
+        a, ret = ops.discount_return(R, V, Tm, TL, LV, 0.99, f, variant=4)
+        np.testing.assert_allclose(a.cpu().numpy(), da, rtol=RTOL, atol=3e-5)
+        np.testing.assert_allclose(ret.cpu().numpy(), dr, rtol=RTOL, atol=3e-5)
+
+
+@pytest.mark.gpu
+def test_gae_tma_rejects_ragged_env_count():
+    import torch
+    from torchrl_b200 import ops
+    z = torch.zeros(4, 100, device="cuda")
+    f = torch.zeros(4, 100, device="cuda", dtype=torch.uint8)
+    with pytest.raises(RuntimeError):
+        ops.gae_scan(z, z, f, f, torch.zeros(100, device="cuda"), 0.99, 0.95, True, variant=4)
+
+
+@pytest.mark.gpu
 def test_gae_full_size_properties():
     """BASELINE size (T=128, N=2**20: 2.4 GB of traffic) through size-independent properties:
-    (1) the vectorised, scalar and serial kernels agree; (2) linearity: GAE is linear in
-    (rewards, values, last_value) for fixed flags; (3) an all-terminal rollout gives adv = r - V."""
+    (1) the TMA-staged (what variant 1 picks at this size), vectorised, scalar and serial kernels agree;
+    (2) linearity: GAE is linear in (rewards, values, last_value) for fixed flags; (3) an all-terminal rollout
+    gives adv = r - V."""
     import torch
     from torchrl_b200 import ops
     T, N = 128, 1 << 20
@@ -96,9 +128,14 @@ def test_gae_full_size_properties():
     a1, r1 = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, variant=1)
     a0, r0 = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, variant=0)
     a3, r3 = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, variant=3)
+    a2v, r2v = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, variant=2)
+    a4v, r4v = ops.gae_scan(R, V, Tm, TL, LV, 0.99, 0.95, True, variant=4)
     torch.testing.assert_close(a1, a0, rtol=RTOL, atol=ATOL)
     torch.testing.assert_close(r1, r0, rtol=RTOL, atol=ATOL)
-    torch.testing.assert_close(a1, a3, rtol=0, atol=0)  # same association, different vector width
+    torch.testing.assert_close(a2v, a3, rtol=0, atol=0)  # same association, different vector width
+    torch.testing.assert_close(a1, a4v, rtol=0, atol=0)  # variant 1 IS the TMA kernel at this size
+    torch.testing.assert_close(a4v, a3, rtol=RTOL, atol=ATOL)
+    torch.testing.assert_close(r4v, r3, rtol=RTOL, atol=ATOL)
     a2, _ = ops.gae_scan(2 * R, 2 * V, Tm, TL, 2 * LV, 0.99, 0.95, True)
     torch.testing.assert_close(a2, 2 * a1, rtol=1e-6, atol=1e-6)
     ones = torch.ones_like(Tm)

@@ -18,75 +18,9 @@
 // later chunks as its carry-in, and replays its TC steps from registers -- the data
 // are read from HBM exactly once (10 B/elt) and written once (8 B/elt): 18 B/elt.
 // HBM-bound; no tensor-core work here.
-#include "common.cuh"
+#include "gae_common.cuh"
 
 namespace trl {
-
-enum { MODE_GAE = 0, MODE_DISC = 1 };
-
-struct GaeParams {
-  const float* __restrict__ rewards;       // (T,N)
-  const float* __restrict__ values;        // (T,N)
-  const uint8_t* __restrict__ terminals;   // (T,N) 0/1
-  const uint8_t* __restrict__ time_limits; // (T,N) 0/1
-  const float* __restrict__ last_value;    // (N)
-  float* __restrict__ advs;                // (T,N)
-  float* __restrict__ rets;                // (T,N)
-  long long T, N;
-  float gamma, gamma_tau;
-  int filter;
-};
-
-template <int VEC> struct VecF;
-template <> struct VecF<1> { using type = float; using flag_t = unsigned char; };
-template <> struct VecF<4> { using type = float4; using flag_t = unsigned; };
-
-template <int VEC> __device__ __forceinline__ void load_f(const float* p, float (&o)[VEC]);
-template <> __device__ __forceinline__ void load_f<1>(const float* p, float (&o)[1]) { o[0] = ld_stream(p); }
-template <> __device__ __forceinline__ void load_f<4>(const float* p, float (&o)[4]) {
-  const float4 v = ld_stream(reinterpret_cast<const float4*>(p));
-  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-}
-template <int VEC> __device__ __forceinline__ unsigned load_flags(const uint8_t* p);
-template <> __device__ __forceinline__ unsigned load_flags<1>(const uint8_t* p) { return ld_stream(p); }
-template <> __device__ __forceinline__ unsigned load_flags<4>(const uint8_t* p) {
-  return ld_stream(reinterpret_cast<const unsigned*>(p));
-}
-template <int VEC> __device__ __forceinline__ void store_f(float* p, const float (&o)[VEC]);
-template <> __device__ __forceinline__ void store_f<1>(float* p, const float (&o)[1]) { st_stream(p, o[0]); }
-template <> __device__ __forceinline__ void store_f<4>(float* p, const float (&o)[4]) {
-  st_stream(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3]));
-}
-
-// per-element affine coefficients
-template <int MODE>
-__device__ __forceinline__ void coeffs(float r, float v, float vnext, unsigned term, unsigned tl, float g, float gt,
-                                       int filter, float& a, float& b) {
-  const float nt = term ? 0.f : 1.f;
-  if (MODE == MODE_GAE) {
-    const float m = (filter && tl) ? 0.f : 1.f;
-    const float delta = r + nt * g * vnext - v;
-    a = m * delta;
-    b = m * gt * nt;
-  } else {
-    if (filter) {
-      const float tlf = tl ? 1.f : 0.f;
-      a = r + tlf * v;
-      b = nt * g * (1.f - tlf);
-    } else {
-      a = r;
-      b = nt * g;
-    }
-  }
-}
-
-// b_t alone (a function of the flags only)
-template <int MODE>
-__device__ __forceinline__ float bcoef(unsigned term, unsigned tl, float g, float gt, int filter) {
-  const float nt = term ? 0.f : 1.f;
-  if (MODE == MODE_GAE) return ((filter && tl) ? 0.f : 1.f) * gt * nt;
-  return filter ? nt * g * (tl ? 0.f : 1.f) : nt * g;
-}
 
 // blockDim = (32, W).  dynamic smem: (2*W + 1) * 32*VEC floats.
 template <int MODE, int VEC, int TC>
@@ -244,6 +178,11 @@ static int dispatch(const GaeParams& p, int variant, cudaStream_t s) {
     gae_serial_kernel<MODE><<<static_cast<unsigned>(ceil_div<long long>(p.N, threads)), threads, 0, s>>>(p);
     return check_launch("gae_serial_kernel");
   }
+  // variant 4 / auto at scale: persistent kernel with TMA-staged tiles (csrc/gae_tma.cu), >= 2 env groups per SM
+  if (variant == 4 || (variant == 1 && p.N >= 2LL * 128 * kNumSM)) {
+    if (gae_tma_supported(p)) return gae_tma_launch(p, MODE, s);
+    if (variant == 4) { set_error("gae: the TMA variant needs N %% 128 == 0 and 16-byte aligned arrays"); return TRL_EUNSUPPORTED; }
+  }
   // VEC=4 needs N % 4 == 0 and 16B/4B-aligned bases; use it once it still fills >= 2 waves of CTAs.
   const bool vec_ok = (p.N % 4 == 0) && aligned16(p.rewards) && aligned16(p.values) && aligned16(p.advs) &&
                       aligned16(p.rets) && aligned16(p.last_value) && aligned4(p.terminals) &&
@@ -265,7 +204,7 @@ TRL_API int trl_gae_scan(const float* rewards, const float* values, const uint8_
   if (T == 0 || N == 0) return TRL_OK;
   TRL_REQUIRE(rewards && values && terminals && time_limits && last_value && advs && returns,
               "trl_gae_scan: null pointer");
-  TRL_REQUIRE(variant >= 0 && variant <= 3, "trl_gae_scan: variant %d not in 0..3", variant);
+  TRL_REQUIRE(variant >= 0 && variant <= 4, "trl_gae_scan: variant %d not in 0..4", variant);
   GaeParams p{rewards, values, terminals, time_limits, last_value, advs, returns, T, N, gamma, gamma * tau,
               time_limit_filter};
   return dispatch<MODE_GAE>(p, variant, static_cast<cudaStream_t>(stream));
@@ -280,7 +219,7 @@ TRL_API int trl_discount_return(const float* rewards, const float* values, const
   if (T == 0 || N == 0) return TRL_OK;
   TRL_REQUIRE(rewards && values && terminals && time_limits && last_value && advs && returns,
               "trl_discount_return: null pointer");
-  TRL_REQUIRE(variant >= 0 && variant <= 3, "trl_discount_return: variant %d not in 0..3", variant);
+  TRL_REQUIRE(variant >= 0 && variant <= 4, "trl_discount_return: variant %d not in 0..4", variant);
   GaeParams p{rewards, values, terminals, time_limits, last_value, advs, returns, T, N, gamma, gamma,
               time_limit_filter};
   return dispatch<MODE_DISC>(p, variant, static_cast<cudaStream_t>(stream));

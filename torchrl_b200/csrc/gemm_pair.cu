@@ -43,7 +43,7 @@ constexpr int kUmmaK = 8;                               // tf32: 32 bytes per MM
 constexpr int kTileBytes = kBM * kBK * 4;               // 16 KB: one (128 x 32) fp32 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;             // 64 KB: A hi | A lo | B hi | B lo
 constexpr int kThreads = 192;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 constexpr int kPitch = kBN + 4;                         // epilogue park pitch (floats): conflict-free rows AND columns
 static_assert(kBM * kPitch * 4 <= kStages * kStageBytes, "epilogue park area must fit in the operand stages");
 
@@ -143,6 +143,22 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                "h"(mask)
                : "memory");
 }
+// explicit shared-state-space accesses: the stage / park pointers are derived from an aligned integer address, which
+// makes plain C++ accesses GENERIC loads / stores that the compiler must order against every global access
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+#ifdef TRL_PAIR_TRACE
+// per-phase clock64() stamps of one CTA (scripts/gemm_probe.py `trace`): slot layout in the probe script
+#define TRL_TRACE(slot) do { if (p.trace && blockIdx.x == p.trace_cta && blockIdx.y == 0) p.trace[(slot)] = clock64(); } while (0)
+#else
+#define TRL_TRACE(slot) do { } while (0)
+#endif
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   unsigned u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
@@ -161,6 +177,10 @@ struct Params {
   float* __restrict__ C;           // (splits, M, 256) when splits > 1 else (M, 256)
   long long M;                     // output rows
   int k_blocks_per_split;          // K blocks (of 32) accumulated by one CTA pair
+#ifdef TRL_PAIR_TRACE
+  long long* trace;
+  unsigned trace_cta;
+#endif
 };
 
 // AMN / BMN: operand is M/N-major (reduction index = row index of the row-major source) instead of K-major.
@@ -181,9 +201,16 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* empty = bars + 2 * kStages;   // [kStages] MMA (multicast commit) -> local TMA
   uint64_t* tmem_full = bars + 3 * kStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+  float* bias_s = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);   // (256) staged once per CTA
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
+  if (threadIdx.x == 0) TRL_TRACE(0);
+  if (warp >= 2 && p.bias) {              // 128 threads x 2 floats
+    const int i = threadIdx.x - 64;
+    bias_s[i] = p.bias[i];
+    bias_s[i + 128] = p.bias[i + 128];
+  }
   const int m_blk = blockIdx.x;           // this CTA's 128 output rows
   const int split = blockIdx.y;
   const int nkb = p.k_blocks_per_split;
@@ -214,6 +241,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   cluster_sync_all();                     // the peer's barriers are initialised before anyone arrives on them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0) TRL_TRACE(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -222,6 +250,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
+        TRL_TRACE(8 + kb);
         mbar_arrive_expect_tx(&full[s], (BSPLIT ? 3 : 2) * kTileBytes);
         const int k0 = (kb0 + kb) * kBK;
         if (!AMN) {
@@ -252,6 +281,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int s = kb % kStages;
         const uint32_t ph = (kb / kStages) & 1;
         mbar_wait(&conv[s], ph);
+        TRL_TRACE(72 + kb);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t da_hi = AMN ? desc_mn_sw128_32b(smem_u32(a_hi(s))) : desc_k_sw128(smem_u32(a_hi(s)));
         const uint64_t da_lo = AMN ? desc_mn_sw128_32b(smem_u32(a_lo(s))) : desc_k_sw128(smem_u32(a_lo(s)));
@@ -267,6 +297,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           umma_pair(tmem_base, da_hi + adv_a, db_hi + adv_b, idesc, 1u);
         }
         umma_commit_multicast(&empty[s], 0b11);            // both CTAs may refill their stage s
+        TRL_TRACE(104 + kb);
       }
       umma_commit_multicast(tmem_full, 0b11);              // both accumulator halves are complete
     }
@@ -277,21 +308,29 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const int s = kb % kStages;
       const uint32_t ph = (kb / kStages) & 1;
       mbar_wait(&full[s], ph);
-      float4* ah = reinterpret_cast<float4*>(a_hi(s));
-      float4* al = reinterpret_cast<float4*>(a_lo(s));
-      float4* bh = reinterpret_cast<float4*>(b_hi(s));
-      float4* bl = reinterpret_cast<float4*>(b_lo(s));
+      if (ct == 0) TRL_TRACE(24 + kb);
+      // all loads of this thread first (independent 16-byte accesses in flight), then convert and store
+      constexpr int kPer = kTileBytes / 16 / 128;          // 8 float4 per thread and tile
+      const uint32_t a_addr = smem_u32(a_hi(s)) + ct * 16, b_addr = smem_u32(b_hi(s)) + ct * 16;
+      float4 va[kPer];
 #pragma unroll
-      for (int i = 0; i < kTileBytes / 16 / 128; ++i) {
-        const int c = ct + i * 128;
+      for (int i = 0; i < kPer; ++i) va[i] = lds128(a_addr + i * 2048);
+#pragma unroll
+      for (int i = 0; i < kPer; ++i) {
         float4 h, l;
-        split4(ah[c], h, l);
-        ah[c] = h;
-        al[c] = l;
-        if (!BSPLIT) {
-          split4(bh[c], h, l);
-          bh[c] = h;
-          bl[c] = l;
+        split4(va[i], h, l);
+        sts128(a_addr + i * 2048, h);
+        sts128(a_addr + kTileBytes + i * 2048, l);
+      }
+      if (!BSPLIT) {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) va[i] = lds128(b_addr + i * 2048);
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) {
+          float4 h, l;
+          split4(va[i], h, l);
+          sts128(b_addr + i * 2048, h);
+          sts128(b_addr + kTileBytes + i * 2048, l);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
@@ -300,55 +339,80 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         if (rank == 0) mbar_arrive_local(&conv[s]);
         else mbar_arrive_remote(&conv[s], 0);
       }
+      if (ct == 0) TRL_TRACE(40 + kb);
     }
     // epilogue: TMEM lane quadrant of this warp = warp % 4.  The operand stages are free now (tmem_full fires after
     // the last MMA of the pair has read them): this warp's 32 rows are parked there with a pitch of 260 floats.
     mbar_wait(tmem_full, 0);
+    if (ct == 0) TRL_TRACE(2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int quad = warp & 3;
-    float* park = reinterpret_cast<float*>(smem) + static_cast<size_t>(quad) * 32 * kPitch;
-#pragma unroll 1
+    const uint32_t park = smem_u32(smem) + static_cast<uint32_t>(quad * 32 * kPitch * 4);
+    const uint32_t my_row = park + static_cast<uint32_t>(lane * kPitch * 4);
+    const uint32_t bias_addr = smem_u32(bias_s);
+    const bool has_bias = p.bias != nullptr;
+    const int act = p.act;
+    const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+#define TRL_TMEM_LD32(R, ADDR)                                                                                        \
+    asm volatile(                                                                                                     \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                     \
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                     \
+        : "=r"(R[0]), "=r"(R[1]), "=r"(R[2]), "=r"(R[3]), "=r"(R[4]), "=r"(R[5]), "=r"(R[6]), "=r"(R[7]), "=r"(R[8]),  \
+          "=r"(R[9]), "=r"(R[10]), "=r"(R[11]), "=r"(R[12]), "=r"(R[13]), "=r"(R[14]), "=r"(R[15]), "=r"(R[16]),      \
+          "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]),     \
+          "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                   \
+        : "r"(ADDR))
+    // two 32-column chunks in flight: the TMEM load of chunk c + 1 is issued before chunk c is processed
+    uint32_t ra[32], rb[32];
+    TRL_TMEM_LD32(ra, taddr0);
+#pragma unroll
     for (int c = 0; c < kBN / 32; ++c) {
-      uint32_t r[32];
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(c * 32);
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      float4* dst = reinterpret_cast<float4*>(park + lane * kPitch + c * 32);
+      uint32_t (&cur)[32] = (c & 1) ? rb : ra;
+      uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
+      if (c + 1 < kBN / 32) TRL_TMEM_LD32(nxt, taddr0 + static_cast<uint32_t>((c + 1) * 32));
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
-        if (p.bias) {   // fused Linear epilogue: z + b, then the activation (same op order as bias_act_fwd_kernel)
-          const float4 b = *reinterpret_cast<const float4*>(p.bias + c * 32 + 4 * j);
+        float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
+                               __uint_as_float(cur[4 * j + 3]));
+        if (has_bias) {   // fused Linear epilogue: z + b, then the activation (same op order as bias_act_fwd_kernel)
+          const float4 b = lds128(bias_addr + static_cast<uint32_t>((c * 32 + 4 * j) * 4));   // broadcast
           v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-          if (p.act == 1) {
+          if (act == 1) {
             v.x = tanh_mufu(v.x); v.y = tanh_mufu(v.y); v.z = tanh_mufu(v.z); v.w = tanh_mufu(v.w);
-          } else if (p.act == 2) {
+          } else if (act == 2) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
         }
-        dst[j] = v;
+        sts128(my_row + static_cast<uint32_t>((c * 32 + 4 * j) * 4), v);
       }
     }
+#undef TRL_TMEM_LD32
+    if (ct == 0) TRL_TRACE(3);
     __syncwarp();                                          // the 32 rows of this warp are complete in shared memory
     const long long row0 = static_cast<long long>(m_blk) * kBM + quad * 32;
     float* cbase = p.C + (static_cast<long long>(split) * p.M + row0) * kBN;
-#pragma unroll 4
-    for (int rr = 0; rr < 32; ++rr) {
-      if (row0 + rr >= p.M) break;
-      const float4* src = reinterpret_cast<const float4*>(park + rr * kPitch);
-      float4* out = reinterpret_cast<float4*>(cbase + static_cast<long long>(rr) * kBN);
-      out[lane] = src[lane];                               // 512 contiguous bytes per warp instruction
-      out[lane + 32] = src[lane + 32];
+    const int nrows = (row0 + 32 <= p.M) ? 32 : static_cast<int>(p.M > row0 ? p.M - row0 : 0);
+#pragma unroll 1
+    for (int r0 = 0; r0 < nrows; r0 += 4) {                // 8 independent 16-byte accesses in flight per thread
+      float4 q[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t src = park + static_cast<uint32_t>(((r0 + u) * kPitch + lane * 4) * 4);
+        q[2 * u] = lds128(src);
+        q[2 * u + 1] = lds128(src + 512);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r0 + u < nrows) {
+          float4* out = reinterpret_cast<float4*>(cbase + static_cast<long long>(r0 + u) * kBN);
+          out[lane] = q[2 * u];                            // 512 contiguous bytes per warp instruction
+          out[lane + 32] = q[2 * u + 1];
+        }
+      }
     }
+    if (ct == 0) TRL_TRACE(4);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -357,6 +421,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
   }
+  if (threadIdx.x == 0) TRL_TRACE(5);
 }
 
 // C[i] = sum_s P[s][i]   (fixed order: 4 interleaved partial sums per element combined pairwise)
@@ -413,6 +478,11 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+#ifdef TRL_PAIR_TRACE
+static long long* g_trace = nullptr;
+static unsigned g_trace_cta = 0;
+#endif
+
 template <bool AMN, bool BMN, bool BSPLIT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const Params& p, unsigned ctas_m,
                   unsigned splits, cudaStream_t st, const char* what) {
@@ -423,12 +493,28 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
     if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
     attr_set = true;
   }
+#ifdef TRL_PAIR_TRACE
+  Params q = p;
+  q.trace = g_trace;
+  q.trace_cta = g_trace_cta;
+  gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, q);
+#else
   gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, p);
+#endif
   return check_launch(what);
 }
 
 }  // namespace pair
 }  // namespace trl
+
+#ifdef TRL_PAIR_TRACE
+// probe builds only (scripts/gemm_probe.py): 136 clock64() slots of CTA `cta` are written to `buf` by every launch
+TRL_API int trl_pair_set_trace(long long* buf, unsigned cta) {
+  trl::pair::g_trace = buf;
+  trl::pair::g_trace_cta = cta;
+  return 0;
+}
+#endif
 
 // C (M x 256) = act(A (M x K) . B + bias) on CTA pairs.  B is the (256 x K) row-major matrix (b_nmajor == 0: C = A B^T,
 // the Linear forward) or the (K x 256) row-major matrix (b_nmajor != 0: C = A B, the dgrad shape).  b_lo == NULL: b_hi is
