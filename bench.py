@@ -15,8 +15,9 @@ Prints ONE JSON line (rank 0).  `value` = device-timed (CUDA events, max over ra
 with the host out of the loop (no per-epoch read-backs); `e2e` = the same metric through the
 public collector/agent API, wall-clock, including every host->device (minibatch row order,
 learning rates) and device->host (per-update logged scalars, episode returns) copy.
-`--impl reference` times the CPU restatement of the reference's path (oracle/ref_port.py --
-the reference itself is pure Python under /root/reference and cannot travel to the GPU box).
+`--impl reference` times the reference's own CPU implementation of the same workload on the box's host cores:
+the unmodified reference classes from oracle/_ref (oracle/build_ref.py copies them there; git-ignored), whole
+epochs timed end to end (oracle/ref_port.py only if no copy of the reference is present).
 """
 import argparse
 import json
@@ -50,6 +51,8 @@ def parse():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0, help="env worker processes of the CPU arm (0 = auto)")
+    ap.add_argument("--cpu-budget-s", type=float, default=900.0,
+                    help="wall-clock budget of the CPU arm; whole epochs are dropped (never shortened) beyond it")
     ap.add_argument("--matmul", default="tc3", choices=["fp32", "tf32x3", "tc3"],
                     help="MLP GEMM path: tc3 = hand-written tcgen05 3xTF32 kernel on the 256-wide layers (default), fp32 = cuBLAS SIMT everywhere, tf32x3 = 3 cuBLAS TF32 GEMMs")
     return ap.parse_args()
@@ -145,51 +148,110 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------- CPU arm
-def cpu_pipeline_sample(env_nums, proc_nums, sample_steps, sample_minibatches, threads):
-    """Bounded sample of the CPU path (oracle/ref_port.py = the reference's algorithm, pinned to it by
-    tests/test_oracle_vs_reference.py): `sample_steps` collector steps over all `env_nums` envs through
-    the multi-process vec env, the Python GAE loop on a full-horizon buffer, and `sample_minibatches`
-    PPO minibatch updates of the full minibatch size.  The per-epoch time is composed from the three
-    measured rates:  T*N/collect_rate + gae + opt_epochs*(T/b)*t_minibatch."""
-    import numpy as np
-    import torch
-    from oracle import ref_port
-    torch.set_num_threads(threads)
-    env, col, agent = ref_port.build_ppo(env_id=ENV_ID, env_nums=env_nums, proc_nums=proc_nums, horizon=HORIZON,
-                                         hidden=HIDDEN, batch_rows=BATCH_ROWS, opt_epochs=OPT_EPOCHS, seed=0)
-    try:
-        col.train_rews = []
-        for _ in range(2):
-            col.step()                                            # warm-up (worker start-up, torch init)
+def workload_string(envs_per_gpu, world):
+    """The ONE description of the workload, printed identically by both arms."""
+    return ("PPO SynthHalfCheetah-v0 (obs 17, act 6), %d envs/GPU x %d GPU, horizon %d, MLP%s, minibatch %d/GPU, "
+            "%d opt epochs (BASELINE.json configs[%d])"
+            % (envs_per_gpu, world, HORIZON, list(HIDDEN), BATCH_ROWS * envs_per_gpu, OPT_EPOCHS, 1 if world == 1 else 4))
+
+
+class _NullLogger:
+    def add_update_info(self, info):
+        pass
+
+    def add_epoch_info(self, *a, **k):
+        pass
+
+    def log(self, *a):
+        pass
+
+    def finish(self):
+        pass
+
+
+class CpuPipeline:
+    """The reference's own CPU path for this workload, whole epochs at a time:
+        collector.train_one_epoch()   T vec-env steps through SubProcVecEnv worker processes (+ NormObs, policy and
+                                      value forward per step)                         collector/on_policy.py:90-153
+        agent.update_per_epoch()      Python GAE loop + opt_epochs x T/b torch-CPU minibatch updates   ppo.py:27-39
+    `kind == "reference"`: the UNMODIFIED reference classes, imported from oracle/_ref (the copy oracle/build_ref.py
+    makes; /root/reference in the build container) behind oracle/shims for the absent third-party modules, over the
+    synthetic gym env of oracle/synth_env.py.  `kind == "port"`: oracle/ref_port.py (pinned bit-for-bit to the
+    reference by tests/test_oracle_vs_reference.py) -- only when no copy of the reference is present."""
+
+    def __init__(self, env_nums, proc_nums, threads, seed=0):
+        import numpy as np
+        import torch
+        from oracle import reference_loader
+        torch.set_num_threads(threads)
+        self.env_nums, self.proc_nums, self.threads = env_nums, proc_nums, threads
+        self.frames = HORIZON * env_nums
+        if reference_loader.available():
+            self.kind = "reference"
+            reference_loader.load()
+            import torchrl.networks as networks
+            import torchrl.policies as policies
+            from torchrl.algo import PPO
+            from torchrl.collector.on_policy import VecOnPolicyCollector
+            from torchrl.env import get_subprocvec_env, get_vec_env
+            from torchrl.replay_buffers.on_policy import OnPolicyReplayBuffer
+            params = {"reward_scale": 1, "obs_norm": True}
+            if proc_nums > 1:
+                env = get_subprocvec_env(ENV_ID, dict(params), env_nums, proc_nums)
+                eval_env = get_vec_env(ENV_ID, dict(params), 1)     # never stepped here; the collector wants one
+            else:
+                env = get_vec_env(ENV_ID, dict(params), env_nums)
+                eval_env = get_vec_env(ENV_ID, dict(params), 1)
+            env.seed(seed)
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            buf = OnPolicyReplayBuffer(env_nums=env_nums, max_replay_buffer_size=HORIZON * env_nums, time_limit_filter=True)
+            net = dict(hidden_shapes=list(HIDDEN), append_hidden_shapes=[], base_type=networks.MLPBase,
+                       activation_func=torch.nn.Tanh)
+            pf = policies.GuassianContPolicyBasicBias(input_shape=OBS_DIM, output_shape=ACT_DIM, tanh_action=True, **net)
+            vf = networks.Net(input_shape=(OBS_DIM,), output_shape=1, **net)
+            col = VecOnPolicyCollector(vf, env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device="cpu",
+                                       train_render=False, epoch_frames=HORIZON * env_nums, max_episode_frames=999,
+                                       eval_episodes=1)
+            self._tmp = tempfile.mkdtemp(prefix="bench_ref_")
+            agent = PPO(pf=pf, vf=vf, plr=3e-4, vlr=3e-4, clip_para=0.2, opt_epochs=OPT_EPOCHS, tau=0.95, shuffle=True,
+                        entropy_coeff=0.005, env=env, replay_buffer=buf, collector=col, logger=_NullLogger(),
+                        discount=0.99, num_epochs=488, batch_size=BATCH_ROWS * env_nums, gae=True, device="cpu",
+                        save_dir=self._tmp)
+            self.env, self.eval_env, self.col, self.agent = env, eval_env, col, agent
+        else:
+            self.kind = "port"
+            from oracle import ref_port
+            env, col, agent = ref_port.build_ppo(env_id=ENV_ID, env_nums=env_nums, proc_nums=proc_nums, horizon=HORIZON,
+                                                 hidden=HIDDEN, batch_rows=BATCH_ROWS, opt_epochs=OPT_EPOCHS, seed=seed)
+            self.env, self.eval_env, self.col, self.agent = env, None, col, agent
+        self.epochs_done = 0
+
+    def epoch(self):
+        """One WHOLE epoch, timed for real: returns (seconds, collect seconds, update seconds)."""
+        self.agent.current_epoch = self.epochs_done
         t0 = time.perf_counter()
-        for _ in range(sample_steps):
-            col.step()
-        t_collect = (time.perf_counter() - t0) / sample_steps     # seconds per vec step
-        # fill the rest of the horizon with copies so GAE / minibatches see full-size float64 buffers
-        buf = agent.buffer
-        while buf.size < buf.rows:
-            buf.add({k: v[(buf.top - 1) % buf.rows] for k, v in buf.data.items() if k not in ("advs", "estimate_returns")})
-        t0 = time.perf_counter()
-        agent.process_epoch_samples()
-        t_gae = time.perf_counter() - t0
-        keys = ["obs", "acts", "advs", "estimate_returns", "values"]
-        it = buf.minibatches(BATCH_ROWS * env_nums, keys, True)
-        agent.update(next(it))                                    # warm-up
-        t0 = time.perf_counter()
-        n = 0
-        for batch in it:
-            agent.update(batch)
-            n += 1
-            if n >= sample_minibatches:
-                break
-        t_mb = (time.perf_counter() - t0) / max(n, 1)
-    finally:
-        env.close()
-    frames = HORIZON * env_nums
-    n_mb = OPT_EPOCHS * (HORIZON // BATCH_ROWS)
-    t_epoch = HORIZON * t_collect + t_gae + n_mb * t_mb
-    return {"env_steps_per_s": frames / t_epoch, "t_epoch_s": t_epoch, "collect_steps_per_s": env_nums / t_collect,
-            "gae_s": t_gae, "minibatch_s": t_mb, "sample_steps": sample_steps, "sample_minibatches": n}
+        self.col.train_one_epoch()
+        t1 = time.perf_counter()
+        self.agent.update_per_epoch()
+        t2 = time.perf_counter()
+        self.epochs_done += 1
+        return t2 - t0, t1 - t0, t2 - t1
+
+    def close(self):
+        for e in (self.env, self.eval_env):
+            try:
+                if e is not None:
+                    e.close()
+            except Exception:
+                pass
+
+    def describe(self):
+        return ("%s: whole epochs timed end to end, each = %d vec-env steps x %d envs over %d env worker processes "
+                "(SubProcVecEnv) + Python GAE + %d PPO minibatches of %d samples on %d torch threads"
+                % ("unmodified reference classes (oracle/_ref)" if self.kind == "reference" else "oracle/ref_port.py",
+                   HORIZON, self.env_nums, self.proc_nums, OPT_EPOCHS * (HORIZON // BATCH_ROWS),
+                   BATCH_ROWS * self.env_nums, self.threads))
 
 
 def auto_procs(env_nums, want=0):
@@ -200,30 +262,24 @@ def auto_procs(env_nums, want=0):
     return max(p, 1), cores
 
 
-def best_torch_threads(cores):
-    """torch intra-op thread count that makes the CPU arm's PPO minibatch fastest on this host.  More
-    threads is not monotonically better (all 128 hyper-threads of the GPU box are ~100x SLOWER than
-    32 for these GEMM sizes), so probe a few counts once and keep the best: the CPU arm gets the most
-    favourable setting, not a pessimised one."""
-    import numpy as np
+def best_torch_threads(cores, batch):
+    """torch intra-op thread count that makes the CPU arm's PPO minibatch fastest on this host.  More threads is
+    not monotonically better (all 128 hyper-threads of the GPU box are ~100x SLOWER than 32 for these GEMM sizes), so
+    probe a few counts once and keep the best: the CPU arm gets the most favourable setting, not a pessimised one."""
     import torch
     import torch.nn as nn
-    from oracle import ref_port
     cands = sorted({c for c in (8, 16, 32, 64, cores // 2, cores) if 1 <= c <= cores})
-    B = BATCH_ROWS * N_ENVS_PER_GPU
-    rs = np.random.RandomState(0)
-    batch = {"obs": rs.randn(B, OBS_DIM), "acts": np.tanh(rs.randn(B, ACT_DIM)), "advs": rs.randn(B, 1),
-             "estimate_returns": rs.randn(B, 1), "values": rs.randn(B, 1)}
+    net = nn.Sequential(nn.Linear(OBS_DIM, HIDDEN[0]), nn.Tanh(), nn.Linear(HIDDEN[0], HIDDEN[1]), nn.Tanh(),
+                        nn.Linear(HIDDEN[1], ACT_DIM))
+    x = torch.randn(batch, OBS_DIM)
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        torch.manual_seed(0)
-        agent = ref_port.PPOPort(ref_port.TanhGaussianPolicy(OBS_DIM, ACT_DIM, list(HIDDEN), nn.Tanh),
-                                 ref_port.MLPNet(OBS_DIM, 1, list(HIDDEN), nn.Tanh), None, batch_size=B)
-        agent.update(batch)
-        t0 = time.perf_counter()
-        agent.update(batch)
-        dt = time.perf_counter() - t0
+        for _ in range(2):
+            net.zero_grad()
+            t0 = time.perf_counter()
+            net(x).square().mean().backward()
+            dt = time.perf_counter() - t0
         if dt < best_t:
             best, best_t = c, dt
         if dt > 4 * best_t:          # past the knee: larger counts only get worse
@@ -232,35 +288,48 @@ def best_torch_threads(cores):
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation on this box's host cores, same workload as our arm.
+    Every step is one whole epoch timed for real (W untimed, then K timed); if the box is so slow that W + K epochs
+    would exceed --cpu-budget-s, fewer are run and `steps` / `warmup` report what was actually done."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    env_nums = args.envs_per_gpu
+    world = max(args.gpus, 1)
+    env_nums = args.envs_per_gpu * world                     # our arm's global env count at this N
     procs, cores = auto_procs(env_nums, args.cpu_procs)
-    threads = best_torch_threads(cores)
-    vals, ms = [], []
-    for i in range(args.warmup + args.steps):
-        r = cpu_pipeline_sample(env_nums, procs, sample_steps=4, sample_minibatches=2, threads=threads)
-        if i >= args.warmup:
-            vals.append(r["env_steps_per_s"])
-            ms.append(r["t_epoch_s"] * 1e3)
-        last = r
-    value = sum(vals) / len(vals)
-    sample = ("per step: 4 collector steps x %d envs over %d spawned env workers + full-horizon Python GAE + 2 PPO "
-              "minibatches of %d samples on %d torch threads; epoch time composed as T*t_step + t_gae + %d*t_minibatch"
-              % (env_nums, procs, BATCH_ROWS * env_nums, threads, OPT_EPOCHS * (HORIZON // BATCH_ROWS)))
+    threads = best_torch_threads(cores, BATCH_ROWS * env_nums)
+    t_start = time.perf_counter()
+    pipe = CpuPipeline(env_nums, procs, threads)
+    try:
+        warm, timed, parts = 0, [], []
+        for i in range(args.warmup):
+            dt, _, _ = pipe.epoch()
+            warm += 1
+            left = args.cpu_budget_s - (time.perf_counter() - t_start)
+            if left < dt * (2 + max(0, args.warmup - 1 - i)):      # keep room for >= 2 timed epochs
+                break
+        for i in range(args.steps):
+            dt, tc, tu = pipe.epoch()
+            timed.append(dt)
+            parts.append((tc, tu))
+            if len(timed) >= 2 and (time.perf_counter() - t_start) + dt > args.cpu_budget_s:
+                break
+    finally:
+        pipe.close()
+    k = len(timed)
+    t_total = sum(timed)
+    value = pipe.frames * k / t_total
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 buffers / f32 nets",
+        "n_gpus": args.gpus, "steps": k, "warmup": warm, "ms_per_step": t_total / k * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 nets / f64 buffers",
         "data": "synthetic",
-        "config": {"workload": "PPO SynthHalfCheetah-v0 (obs 17, act 6), %d envs, horizon %d, MLP%s, "
-                               "batch %d, %d opt epochs" % (env_nums, HORIZON, list(HIDDEN), BATCH_ROWS * env_nums,
-                                                            OPT_EPOCHS),
+        "config": {"workload": workload_string(args.envs_per_gpu, world), "global_envs": env_nums,
                    "parallelism": "cpu: %d env worker processes, %d torch threads" % (procs, threads)},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": max(procs, threads), "host_logical_cores": cores,
-                         "kind": "port", "sample": sample,
-                         "detail": {k: last[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s")}},
+                         "kind": pipe.kind, "sample": pipe.describe() + "; %d warm-up + %d timed epochs" % (warm, k),
+                         "detail": {"epoch_s": timed, "collect_s": [p[0] for p in parts], "update_s": [p[1] for p in parts],
+                                    "requested_steps": args.steps, "requested_warmup": args.warmup}},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -376,9 +445,11 @@ def run_ours(args):
             agent.update_per_epoch()
         else:
             col.rollout_no_sync()
-            if ctx.world_size > 1:
-                # keep the ranks' launch queues short and aligned before the collective-bearing update graphs
-                torch.cuda.current_stream(device).synchronize()
+            # bound the launch queue (no data copied): the public-API leg waits here too (it reads the episode
+            # count), and a queue holding the rollout's 128 AND the update's 320 graph launches measured ~8 % slower
+            # on B200 than two shorter ones; with several ranks this also aligns them before the collective-bearing
+            # update graphs
+            torch.cuda.current_stream(device).synchronize()
             agent.update_per_epoch(flush_infos=False)
 
     # one nvidia-smi poller for the whole job (rank 0's GPU), started now so that its start-up is over before
@@ -449,31 +520,30 @@ def run_ours(args):
     cpu_baseline = None
     if ctx.rank == 0 and args.gpus == 1 and not args.skip_cpu_baseline:
         procs, cores = auto_procs(args.envs_per_gpu, args.cpu_procs)
-        threads = best_torch_threads(cores)
-        r = cpu_pipeline_sample(args.envs_per_gpu, procs, sample_steps=6, sample_minibatches=3, threads=threads)
-        cpu_baseline = {"value": r["env_steps_per_s"], "unit": "env-steps/s", "cores": max(procs, threads),
-                        "host_logical_cores": cores, "kind": "port",
-                        "sample": "6 collector steps x %d envs over %d spawned env workers + full-horizon Python GAE "
-                                  "+ 3 PPO minibatches of %d samples (%d torch threads = fastest of a probe; host has %d "
-                                  "logical cores); epoch time composed from the three rates"
-                                  % (args.envs_per_gpu, procs, BATCH_ROWS * args.envs_per_gpu, threads, cores),
-                        "detail": {k: r[k] for k in ("collect_steps_per_s", "gae_s", "minibatch_s", "t_epoch_s")}}
+        threads = best_torch_threads(cores, BATCH_ROWS * args.envs_per_gpu)
+        pipe = CpuPipeline(args.envs_per_gpu, procs, threads)
+        try:
+            dt, tc, tu = pipe.epoch()                       # ONE whole epoch, timed for real (~20-30 s of CPU work)
+        finally:
+            pipe.close()
+        cpu_baseline = {"value": pipe.frames / dt, "unit": "env-steps/s", "cores": max(procs, threads),
+                        "host_logical_cores": cores, "kind": pipe.kind,
+                        "sample": pipe.describe() + "; 1 epoch, no warm-up epoch (the reference arm, --impl reference, "
+                                                    "times warm epochs)",
+                        "detail": {"epoch_s": dt, "collect_s": tc, "update_s": tu}}
 
     if ctx.rank == 0:
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": ctx.world_size,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_dev / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "PPO SynthHalfCheetah-v0 (obs 17, act 6), %d envs/GPU x %d GPU, horizon %d, "
-                                   "MLP%s, minibatch %d/GPU, %d opt epochs (BASELINE.json configs[%d])"
-                                   % (args.envs_per_gpu, ctx.world_size, HORIZON, list(HIDDEN),
-                                      BATCH_ROWS * args.envs_per_gpu, OPT_EPOCHS, 1 if ctx.world_size == 1 else 4),
+            "config": {"workload": workload_string(args.envs_per_gpu, ctx.world_size),
                        "global_envs": args.envs_per_gpu * ctx.world_size,
                        "parallelism": "dp%d (env sharding, NCCL all-reduce of the flat gradient)" % ctx.world_size,
                        "matmul": {"fp32": "fp32 cuBLAS SIMT (TF32 off)",
                                   "tf32x3": "3xTF32 error-compensated tensor-core GEMMs (fp32-faithful), cuBLAS",
-                                  "tc3": "256-wide layers: hand-written tcgen05 3xTF32 GEMM (fp32-faithful, "
-                                         "csrc/gemm_tf32x3.cu); 17-wide / <=8-wide layers: HBM-bound fp32 kernels (csrc/skinny.cu)"}[args.matmul], "cuda_graphs": not args.no_graph,
+                                  "tc3": "256-wide layers: hand-written tcgen05 3xTF32 GEMM on CTA pairs (fp32-faithful, "
+                                         "csrc/gemm_pair.cu); 17-wide / <=8-wide layers: HBM-bound fp32 kernels (csrc/skinny.cu)"}[args.matmul], "cuda_graphs": not args.no_graph,
                        "l2": "each step rewrites the whole 100 MB rollout working set and all activations "
                              "(> 126 MB L2 per epoch); the GAE roofline launch flushes L2 explicitly"},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -1,8 +1,9 @@
-"""Import the unmodified reference (RchalYang/torchrl) from /root/reference.
+"""Import the unmodified reference (RchalYang/torchrl): from /root/reference where it is mounted (the build
+container), else from oracle/_ref -- the byte-for-byte copy oracle/build_ref.py places beside the oracle so
+that it travels to the GPU box (git-ignored: reference sources never enter this repository's history).
 
-TEST INFRASTRUCTURE ONLY.  Works in the build container (where /root/reference
-is mounted read-only); on the GPU box the directory does not exist and
-``available()`` is False -- nothing that runs there may depend on it.
+TEST / BASELINE INFRASTRUCTURE ONLY.  ``available()`` is False when neither location exists; nothing in the
+product may depend on it.
 
 The reference imports third-party modules that are absent from this image
 (gym, toolz, tensorboardX, wandb -- SURVEY.md Appendix C); oracle/shims holds
@@ -14,8 +15,17 @@ workers are spawned and re-import everything
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("TORCHRL_REFERENCE_ROOT", "/root/reference")
 _HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    for cand in (os.environ.get("TORCHRL_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "torchrl")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 SHIMS = os.path.join(_HERE, "shims")
 REPO_ROOT = os.path.dirname(_HERE)
 

@@ -80,7 +80,8 @@ def trace_case():
             print("   full seen   " + " ".join("%6d" % rel(24 + k) for k in range(nkb)))
             print("   conv done   " + " ".join("%6d" % rel(40 + k) for k in range(nkb)))
             print("   mma start   " + " ".join("%6d" % rel(72 + k) for k in range(nkb)))
-            print("   mma issued  " + " ".join("%6d" % rel(104 + k) for k in range(nkb)), flush=True)
+            print("   mma issued  " + " ".join("%6d" % rel(104 + k) for k in range(nkb)))
+            print("   epi chunk   " + " ".join("%6d" % rel(120 + k) for k in range(8)), flush=True)
 
     show("nt split + tanh", lambda: lib.trl_gemm3_pair(a.data_ptr(), hi.data_ptr(), lo.data_ptr(), out.data_ptr(), M, K, 0,
                                                         bias.data_ptr(), 1, st))

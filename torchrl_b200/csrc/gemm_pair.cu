@@ -17,8 +17,8 @@
 //   * B may be N-major (b_nmajor): the dgrad shape dX = G . W reads W (K x 256, row-major) directly -- no per-
 //     minibatch transpose of the weights;
 //   * a 64 KB stage instead of 96 KB -> 3-stage ring;
-//   * the epilogue parks the tile in the (free) operand stages and stores 512 contiguous bytes per warp
-//     instruction; tanh = 1 - 2/(exp(2x)+1) on the MUFU unit (abs err < 2e-7, same as csrc/skinny.cu).
+//   * the epilogue streams 32 columns at a time through a warp-private transposition buffer and stores whole
+//     128-byte row segments; tanh = 1 - 2/(exp(2x)+1) on the MUFU unit (abs err < 2e-7, same as csrc/skinny.cu).
 // Shapes (one template each):
 //   nt   : A (M x K) row-major, B (256 x K) row-major      forward  y = act(x W^T + b)
 //   nn   : A (M x K) row-major, B (K x 256) row-major      dgrad    dX = G W
@@ -44,8 +44,6 @@ constexpr int kTileBytes = kBM * kBK * 4;               // 16 KB: one (128 x 32)
 constexpr int kStageBytes = 4 * kTileBytes;             // 64 KB: A hi | A lo | B hi | B lo
 constexpr int kThreads = 192;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
-constexpr int kPitch = kBN + 4;                         // epilogue park pitch (floats): conflict-free rows AND columns
-static_assert(kBM * kPitch * 4 <= kStages * kStageBytes, "epilogue park area must fit in the operand stages");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -60,8 +58,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+// NOTE on scopes: explicit `.release.cluster` / `.acquire.cluster` qualifiers compile to MEMBAR.ALL.GPU + ERRBAR on
+// every arrive and CCTL.IVALL (L1 invalidate) after every wait -- measured at ~1.4 k cycles per K block in the
+// converter loop (profiles/pair_gemm_r2.md).  The data these barriers order is shared memory handed to the async
+// proxy (fence.proxy.async before the arrive) and TMEM (tcgen05 fences), so the default CTA-scope semantics that
+// CUTLASS' ClusterBarrier uses are sufficient.
 __device__ __forceinline__ void mbar_arrive_local(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
@@ -69,7 +72,7 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
       "{\n\t"
       ".reg .b32 remote;\n\t"
       "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t"
       "}" ::"r"(smem_u32(bar)),
       "r"(rank)
       : "memory");
@@ -77,14 +80,13 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// cluster-scope acquire: the barrier may have been completed by arrivals / commits of the peer CTA
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
@@ -206,10 +208,10 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   if (threadIdx.x == 0) TRL_TRACE(0);
-  if (warp >= 2 && p.bias) {              // 128 threads x 2 floats
-    const int i = threadIdx.x - 64;
-    bias_s[i] = p.bias[i];
-    bias_s[i + 128] = p.bias[i + 128];
+  float bias_r0 = 0.f, bias_r1 = 0.f;     // 128 epilogue threads x 2 floats, parked in shared memory after the set-up
+  if (warp >= 2 && p.bias) {
+    bias_r0 = p.bias[threadIdx.x - 64];
+    bias_r1 = p.bias[threadIdx.x + 64];
   }
   const int m_blk = blockIdx.x;           // this CTA's 128 output rows
   const int split = blockIdx.y;
@@ -304,6 +306,8 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else {
     // ------------------------------------------------------------------ converters (warps 2..5), then epilogue
     const int ct = threadIdx.x - 64;                       // 0..127
+    bias_s[ct] = bias_r0;
+    bias_s[ct + 128] = bias_r1;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (kb / kStages) & 1;
@@ -343,16 +347,26 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     // epilogue: TMEM lane quadrant of this warp = warp % 4.  The operand stages are free now (tmem_full fires after
     // the last MMA of the pair has read them): this warp's 32 rows are parked there with a pitch of 260 floats.
+    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps: bias_s is complete
     mbar_wait(tmem_full, 0);
     if (ct == 0) TRL_TRACE(2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // Streaming epilogue, 32 columns at a time: TMEM -> registers (this thread = one accumulator row) -> bias /
+    // activation -> a warp-private (32 x 36) transposition buffer in the free operand stages -> global memory as
+    // 128-byte row segments (one 16-byte piece per lane, 4 rows per store instruction: every 32-byte sector written
+    // whole).  Stores of chunk c overlap the TMEM load and the MUFU work of chunk c + 1.
     const int quad = warp & 3;
-    const uint32_t park = smem_u32(smem) + static_cast<uint32_t>(quad * 32 * kPitch * 4);
-    const uint32_t my_row = park + static_cast<uint32_t>(lane * kPitch * 4);
+    constexpr int kTP = 36;                                // floats: conflict-free for the row-wise STS.128 AND LDS.128
+    const uint32_t tbuf = smem_u32(smem) + static_cast<uint32_t>(quad * 32 * kTP * 4);
+    const uint32_t my_row = tbuf + static_cast<uint32_t>(lane * kTP * 4);
+    const uint32_t rd = tbuf + static_cast<uint32_t>(((lane >> 3) * kTP + (lane & 7) * 4) * 4);
     const uint32_t bias_addr = smem_u32(bias_s);
     const bool has_bias = p.bias != nullptr;
     const int act = p.act;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    const long long row0 = static_cast<long long>(m_blk) * kBM + quad * 32;
+    float* cbase = p.C + (static_cast<long long>(split) * p.M + row0 + (lane >> 3)) * kBN + (lane & 7) * 4;
+    const int nrows = (row0 + 32 <= p.M) ? 32 : static_cast<int>(p.M > row0 ? p.M - row0 : 0);
 #define TRL_TMEM_LD32(R, ADDR)                                                                                        \
     asm volatile(                                                                                                     \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
@@ -363,7 +377,6 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           "=r"(R[17]), "=r"(R[18]), "=r"(R[19]), "=r"(R[20]), "=r"(R[21]), "=r"(R[22]), "=r"(R[23]), "=r"(R[24]),     \
           "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                   \
         : "r"(ADDR))
-    // two 32-column chunks in flight: the TMEM load of chunk c + 1 is issued before chunk c is processed
     uint32_t ra[32], rb[32];
     TRL_TMEM_LD32(ra, taddr0);
 #pragma unroll
@@ -372,6 +385,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t (&cur)[32] = (c & 1) ? rb : ra;
       uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
       if (c + 1 < kBN / 32) TRL_TMEM_LD32(nxt, taddr0 + static_cast<uint32_t>((c + 1) * 32));
+      __syncwarp();                                        // the previous chunk has been read out of the buffer
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
@@ -385,33 +399,20 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
         }
-        sts128(my_row + static_cast<uint32_t>((c * 32 + 4 * j) * 4), v);
+        sts128(my_row + static_cast<uint32_t>(j * 16), v);
       }
+      __syncwarp();
+      float4 q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = lds128(rd + static_cast<uint32_t>(i * 4 * kTP * 4));   // rows 4 i + lane / 8
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (4 * i + (lane >> 3) < nrows)
+          *reinterpret_cast<float4*>(cbase + static_cast<long long>(4 * i) * kBN + c * 32) = q[i];
+      if (ct == 0) TRL_TRACE(120 + c);
     }
 #undef TRL_TMEM_LD32
     if (ct == 0) TRL_TRACE(3);
-    __syncwarp();                                          // the 32 rows of this warp are complete in shared memory
-    const long long row0 = static_cast<long long>(m_blk) * kBM + quad * 32;
-    float* cbase = p.C + (static_cast<long long>(split) * p.M + row0) * kBN;
-    const int nrows = (row0 + 32 <= p.M) ? 32 : static_cast<int>(p.M > row0 ? p.M - row0 : 0);
-#pragma unroll 1
-    for (int r0 = 0; r0 < nrows; r0 += 4) {                // 8 independent 16-byte accesses in flight per thread
-      float4 q[8];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t src = park + static_cast<uint32_t>(((r0 + u) * kPitch + lane * 4) * 4);
-        q[2 * u] = lds128(src);
-        q[2 * u + 1] = lds128(src + 512);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (r0 + u < nrows) {
-          float4* out = reinterpret_cast<float4*>(cbase + static_cast<long long>(r0 + u) * kBN);
-          out[lane] = q[2 * u];                            // 512 contiguous bytes per warp instruction
-          out[lane + 32] = q[2 * u + 1];
-        }
-      }
-    }
     if (ct == 0) TRL_TRACE(4);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
