@@ -508,7 +508,8 @@ def run_ours(args):
         pj = os.path.join(ROOT, "profiles", "gae_scan_ncu_summary.json")
         if os.path.exists(pj):
             traffic = json.load(open(pj)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "gae_chunked_kernel<GAE,VEC=4,TC=4>", "bound": "hbm",
+        roofline = {"kernel": "gae_tma_kernel<GAE> (csrc/gae_tma.cu: persistent, TMA-staged tiles; what trl_gae_scan "
+                              "launches at this size)", "bound": "hbm",
                     "workload": "T=128 x N=2^20 rollout (2.42 GB algorithmic), L2 flushed between launches",
                     "achieved": alg_bytes / dur / 1e9, "peak": peak, "peak_source": how, "unit": "GB/s",
                     "frac": alg_bytes / dur / 1e9 / peak, "traffic": traffic,
