@@ -191,6 +191,32 @@ int trl_per_update(float* prio, const int64_t* idx, const float* td, int b, int 
                    float* max_prio, void* stream);
 int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void* stream);
 
+/* ---- K12: one-shot all-reduce over NVLink peer memory (csrc/comm.cu; no reference counterpart).
+ * Communication buffers are cudaMalloc blocks of their own (cudaIpc needs that): the ONLY allocations this library
+ * makes.  peer_data / peer_flags: host arrays of `world` device pointers, entry r = rank r's operand buffer / flag
+ * pad (trl_comm_flag_bytes() bytes, zero-initialised) as mapped in THIS process (own entries = local pointers).
+ * `seq`: device uint32 of the communicator, starts at 0, bumped by every call; all ranks must issue the same calls in
+ * the same order.  Sums run in rank order: every rank obtains the bit-identical result. */
+int trl_comm_flag_bytes(void);
+int trl_comm_ipc_handle_bytes(void);
+int trl_comm_alloc(int64_t bytes, void** ptr_out);
+int trl_comm_free(void* ptr);
+int trl_comm_ipc_get(void* ptr, void* handle_out);
+int trl_comm_ipc_open(const void* handle, void** ptr_out);
+int trl_comm_ipc_close(void* ptr);
+int trl_comm_scratch_doubles(int nseg);
+/* out (n) = sum over ranks of the flat gradient + what trl_grad_sumsq computes for `out` (per-segment sum of squares,
+ * Adam step counts, bias corrections): the all-reduce before clip_grad_norm_ of ppo.py:72,117 and the norm itself in
+ * one kernel.  zero_local: this rank's operand is zeroed once every peer has read it. */
+int trl_allreduce_grad(const void* const* peer_data, void* const* peer_flags, int rank, int world, float* out,
+                       int64_t n, const int64_t* seg_begin_host, int nseg, unsigned active_mask, double* sumsq3_out,
+                       int* step_counts, double beta1, double beta2, double* scratch, unsigned* ticket, unsigned* seq,
+                       int zero_local, void* stream);
+/* fp64 moment vectors (observation-normaliser sums of base_wrapper.py:75-82, advantage moments of ppo.py:147):
+ * gather == 0: out (n) = sum over ranks; gather != 0: out (world, n) = every rank's vector in rank order. */
+int trl_allreduce_f64(const void* const* peer_data, void* const* peer_flags, int rank, int world, double* out, int n,
+                      int gather, unsigned* seq, void* stream);
+
 /* ---- fp32-faithful tensor-core GEMM for the 256-wide MLP layers (tcgen05.mma kind::tf32, 3xTF32 split in
  * shared memory, TMA operand loads, TMEM accumulator): C (M x 256) = A (M x K) . B (256 x K)^T, A/B row-major.
  * Serves MLPBase's Linear forward / dgrad / wgrad (networks/base.py:24-44) when the layer width is 256.

@@ -65,6 +65,16 @@ SIGNATURES = {
     "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp, i32, vp],
     "trl_gemm_tf32x3_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_transpose_f32": [vp, vp, i64, i32, vp],
+    "trl_comm_flag_bytes": [],
+    "trl_comm_ipc_handle_bytes": [],
+    "trl_comm_alloc": [i64, vp],
+    "trl_comm_free": [vp],
+    "trl_comm_ipc_get": [vp, vp],
+    "trl_comm_ipc_open": [vp, vp],
+    "trl_comm_ipc_close": [vp],
+    "trl_comm_scratch_doubles": [i32],
+    "trl_allreduce_grad": [vp, vp, i32, i32, vp, i64, vp, i32, u32, vp, vp, f64, f64, vp, vp, vp, i32, vp],
+    "trl_allreduce_f64": [vp, vp, i32, i32, vp, i32, i32, vp, vp],
     "trl_gemm3_pair": [vp, vp, vp, vp, i64, i64, i32, vp, i32, vp],
     "trl_gemm3_pair_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_skinny_k_fwd": [vp, vp, vp, vp, i64, i32, i32, i32, vp],
@@ -91,7 +101,8 @@ _RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles":
              "trl_skinny_tn_scratch_floats": ctypes.c_int64,
              "trl_skinny_dgrad_act_scratch_floats": ctypes.c_int64}
 # entry points that return a value rather than an error code
-_VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas",
+_VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas", "trl_comm_flag_bytes",
+                "trl_comm_ipc_handle_bytes", "trl_comm_scratch_doubles",
                 "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")
 
 _lib = None

@@ -30,7 +30,7 @@ class DDPG(OffRLAlgo):
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("torchrl_b200 fuses clip+Adam in CUDA; only optim.Adam is supported")
         clip = self.grad_clip if self.grad_clip else 0.0
-        self.opt = FlatAdam([self.pf, self.qf], lrs=[plr, qlr], eps=1e-8, max_norms=[clip] * 2, device=self.device)
+        self.opt = FlatAdam([self.pf, self.qf], lrs=[plr, qlr], eps=1e-8, max_norms=[clip] * 2, device=self.device, dist=self.dist)
         self.pf_optimizer = SegmentOptimizer(self.opt, 0)
         self.qf_optimizer = SegmentOptimizer(self.opt, 1)
         self._target_flat = FlatParams([self.target_pf, self.target_qf], device=self.device)

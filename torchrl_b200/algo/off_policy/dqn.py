@@ -32,7 +32,7 @@ class DQN(OffRLAlgo):
             raise NotImplementedError("torchrl_b200 fuses Adam in CUDA; only optim.Adam is supported "
                                       "(the reference's dqn_pong config uses RMSprop: out of this round's scope)")
         eps = optimizer_info.get("eps", 1e-8)
-        self.opt = FlatAdam([self.qf], lrs=[qlr], eps=eps, max_norms=[0.0], device=self.device)
+        self.opt = FlatAdam([self.qf], lrs=[qlr], eps=eps, max_norms=[0.0], device=self.device, dist=self.dist)
         self.qf_optimizer = SegmentOptimizer(self.opt, 0)
         self._target_flat = FlatParams([self.target_qf], device=self.device)
         self.obs_scale = getattr(self.env, "obs_scale", None)

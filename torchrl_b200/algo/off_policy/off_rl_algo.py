@@ -78,8 +78,8 @@ class OffRLAlgo(RLAlgo):
         indices from the same host seed): the flat gradient is summed over ranks first and scaled by 1/G inside
         the Adam kernel, before clipping -- what a single process over all envs would apply.  NOT yet exercised on
         more than one GPU (the single-process path is unchanged)."""
-        scale = self.dist.all_reduce_grads(self.opt.grad) if self._dp else 1.0
-        self.opt.step(active_mask=active_mask, grad_scale=scale)
+        scale, fused_norm = self.dist.reduce_grads(self.opt, active_mask) if self._dp else (1.0, False)
+        self.opt.step(active_mask=active_mask, grad_scale=scale, reduced=fused_norm)
 
     def _all_ranks(self, vec):
         """Concatenation of a per-rank (B,) vector over ranks (rank order), identical on every rank."""

@@ -35,7 +35,7 @@ class TD3(OffRLAlgo):
             raise NotImplementedError("torchrl_b200 fuses clip+Adam in CUDA; only optim.Adam is supported")
         clip = self.grad_clip if self.grad_clip else 0.0
         self.opt = FlatAdam([self.pf, self.qf1, self.qf2], lrs=[plr, qlr, qlr], eps=1e-8, max_norms=[clip] * 3,
-                            device=self.device)
+                            device=self.device, dist=self.dist)
         self.pf_optimizer = SegmentOptimizer(self.opt, 0)
         self.qf1_optimizer = SegmentOptimizer(self.opt, 1)
         self.qf2_optimizer = SegmentOptimizer(self.opt, 2)

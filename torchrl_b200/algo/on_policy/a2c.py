@@ -24,7 +24,7 @@ class A2C(OnRLAlgo):
             raise NotImplementedError("torchrl_b200 fuses clip+Adam in CUDA; only optim.Adam is supported")
         self.optimizer_class = optimizer_class
         # segment 0 = policy, segment 1 = value net
-        self.opt = FlatAdam([self.pf, self.vf], lrs=[plr, vlr], eps=1e-5, max_norms=[0.5, 0.5], device=self.device)
+        self.opt = FlatAdam([self.pf, self.vf], lrs=[plr, vlr], eps=1e-5, max_norms=[0.5, 0.5], device=self.device, dist=self.dist)
         self.pf_optimizer = SegmentOptimizer(self.opt, 0)
         self.vf_optimizer = SegmentOptimizer(self.opt, 1)
         self.entropy_coeff = entropy_coeff

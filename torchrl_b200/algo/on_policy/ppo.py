@@ -131,10 +131,10 @@ class PPO(A2C):
                                              self.entropy_coeff, self.tanh_action, st["scratch"], info=info[0:16])
         torch.autograd.backward([mean, log_std], [g_mean, g_ls])
         # gradient exchange (multi-GPU) + clip + Adam + zero_grad
-        scale = 1.0
+        scale, fused_norm = 1.0, False
         if self.dist is not None:
-            scale = self.dist.all_reduce_grads(self.opt.grad)
-        self.opt.step(grad_scale=scale)
+            scale, fused_norm = self.dist.reduce_grads(self.opt)
+        self.opt.step(grad_scale=scale, reduced=fused_norm)
         # per-update log row, device counters
         ops.ring_write(st["log_plan"], st["upd"])
         ops.counter_advance(None, st["upd"], st["U"])
@@ -234,10 +234,10 @@ class PPO(A2C):
                                              self.clip_para, self.entropy_coeff, self.tanh_action, scratch,
                                              info=info32[0:16])
         torch.autograd.backward([mean, log_std], [g_mean, g_ls])
-        scale = 1.0
+        scale, fused_norm = 1.0, False
         if self.dist is not None:
-            scale = self.dist.all_reduce_grads(self.opt.grad)
-        self.opt.step(grad_scale=scale)
+            scale, fused_norm = self.dist.reduce_grads(self.opt)
+        self.opt.step(grad_scale=scale, reduced=fused_norm)
         row = info32.cpu().numpy()
         norms = self.opt.grad_norms().cpu().numpy() * scale
         info = {k: float(row[20 + i]) for i, k in enumerate(_ADV_KEYS)}

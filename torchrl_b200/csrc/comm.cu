@@ -1,0 +1,295 @@
+// comm.cu -- K12: one-shot all-reduce over NVLink peer memory, fused with the gradient-norm reduction.
+//
+// The reference is single-process (no collective anywhere); data-parallel PPO needs, per
+// minibatch, the SUM over ranks of the flat pf|vf gradient (570 KB at MLP(256,256)) followed by the per-network
+// global norm that clip_grad_norm_ uses (/root/reference/torchrl/algo/on_policy/ppo.py:72,117), and per collector
+// step / per epoch a few hundred bytes of fp64 moments.  All of these are LATENCY-bound: NCCL's ring / tree launch
+// costs ~25-40 us per call on 8 GPUs, more than the 6 us the bytes need on NVLink 5.
+//
+// One kernel does the exchange AND the reduction that follows it:
+//   * every rank keeps its operand in a buffer that all peers have mapped (cudaIpc handles, exchanged once);
+//   * block b of every rank raises flag[ready][b][rank] in all peers' flag pads (st.release.sys) and waits for the W
+//     flags in its own pad: "everybody's operand is complete";
+//   * each thread sums its float4 / double slice over the W peer buffers IN RANK ORDER (so every rank computes the
+//     bit-identical result -- parameters never drift apart, no broadcast needed), writes the sum to a local output
+//     buffer and, for the gradient, accumulates the per-segment sum of squares in fp64 (two-level, fixed order: the
+//     role of csrc/optim.cu's grad_sumsq_kernel, incl. Adam step counts and bias corrections in the last block);
+//   * block b raises flag[done][b][rank] everywhere and waits: "everybody has finished reading my operand", then
+//     zeroes its slice of the local operand (the gradient buffer is accumulated into by the next backward).
+// Flags carry a sequence number that only grows (kept in device memory, bumped by the last block), so nothing is
+// ever reset.  grid <= 64 blocks: all co-resident, the peer waits cannot deadlock on scheduling.
+// Evidence in SASS: LDG / STG with .SYS scope on peer (IPC-mapped) addresses in the same kernel as the reduction.
+#include "common.cuh"
+
+namespace trl {
+namespace comm {
+
+constexpr int kMaxWorld = 8;
+constexpr int kMaxBlocks = 64;
+constexpr int kThreads = 256;
+constexpr int kMaxSeg = 8;
+constexpr int kFlagWords = 2 * kMaxBlocks * kMaxWorld;    // [phase][block][source rank] uint32
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_peer_f64(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+
+struct Peers {
+  const void* data[kMaxWorld];     // operand buffer of every rank (own entry = local pointer)
+  unsigned* flags[kMaxWorld];      // flag pad of every rank (kFlagWords uint32)
+};
+
+// all blocks of all ranks: raise my flag of `phase` in every pad, wait for every rank's flag in my pad
+__device__ __forceinline__ void cross_rank_barrier(const Peers& pe, int rank, int world, int phase, unsigned seq) {
+  const int slot = (phase * kMaxBlocks + blockIdx.x) * kMaxWorld;
+  __syncthreads();                                     // every thread of this block is done with the previous stage
+  if (threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys(pe.flags[threadIdx.x] + slot + rank, seq);
+    const unsigned* mine = pe.flags[rank] + slot + threadIdx.x;
+    while (static_cast<int>(ld_acquire_sys(mine) - seq) < 0) { }
+  }
+  __syncthreads();
+}
+
+struct SegTable {
+  long long begin[kMaxSeg + 1];
+  int nseg;
+};
+
+struct GradParams {
+  Peers pe;
+  int rank, world;
+  float* __restrict__ local;       // this rank's operand (= pe.data[rank]), zeroed at the end when zero_local
+  float* __restrict__ out;         // (n) reduced gradient (SUM over ranks)
+  long long n;                     // floats, a multiple of 4
+  SegTable seg;
+  unsigned active_mask;
+  double* __restrict__ partial;    // (gridDim.x * nseg) scratch
+  double* __restrict__ sumsq3;     // (3 nseg): sum of squares, then (1 - b1^t, sqrt(1 - b2^t)) per segment
+  int* __restrict__ step;          // (nseg) Adam step counts (bumped here), may be null
+  double beta1, beta2;
+  unsigned* __restrict__ ticket;
+  unsigned* __restrict__ seq;      // device sequence number of this communicator
+  int zero_local;
+};
+
+__global__ void __launch_bounds__(kThreads) allreduce_grad_kernel(const GradParams p) {
+  __shared__ double sh[kThreads / 32][kMaxSeg];
+  __shared__ unsigned s_last;
+  const unsigned seq = *p.seq + 1u;
+  cross_rank_barrier(p.pe, p.rank, p.world, 0, seq);
+  // ---- reduce my slice over the ranks, in rank order -------------------------------------------------------------
+  const long long n4 = p.n >> 2;
+  const long long per = ceil_div<long long>(n4, gridDim.x);
+  const long long lo = per * blockIdx.x, hi = (lo + per < n4) ? lo + per : n4;
+  double acc[kMaxSeg];
+#pragma unroll
+  for (int s = 0; s < kMaxSeg; ++s) acc[s] = 0.0;
+  for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
+    float4 v = ld_peer_f4(static_cast<const float*>(p.pe.data[0]) + 4 * i);
+    for (int r = 1; r < p.world; ++r) {
+      const float4 w = ld_peer_f4(static_cast<const float*>(p.pe.data[r]) + 4 * i);
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    *reinterpret_cast<float4*>(p.out + 4 * i) = v;
+    // segments start on 16-byte boundaries (flat.py), so a float4 never straddles two of them
+    int s = 0;
+#pragma unroll
+    for (int k = 1; k < kMaxSeg; ++k) s += (k < p.seg.nseg && 4 * i >= p.seg.begin[k]) ? 1 : 0;
+    const double q = static_cast<double>(v.x) * v.x + static_cast<double>(v.y) * v.y + static_cast<double>(v.z) * v.z +
+                     static_cast<double>(v.w) * v.w;
+#pragma unroll
+    for (int k = 0; k < kMaxSeg; ++k) acc[k] += (k == s) ? q : 0.0;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kMaxSeg; ++k) {
+    const double t = warp_sum(acc[k]);
+    if (lane == 0) sh[wid][k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < p.seg.nseg) {
+    double t = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
+    p.partial[blockIdx.x * p.seg.nseg + threadIdx.x] = t;
+  }
+  // ---- everybody has read my operand: it may be overwritten ------------------------------------------------------------
+  cross_rank_barrier(p.pe, p.rank, p.world, 1, seq);
+  if (p.zero_local)
+    for (long long i = lo + threadIdx.x; i < hi; i += kThreads)
+      *reinterpret_cast<float4*>(p.local + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // ---- last block: per-segment totals, Adam step counts, bias corrections, sequence number --------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x < p.seg.nseg) {
+    const int k = threadIdx.x;
+    if ((p.active_mask >> k) & 1u) {
+      double t = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[b * p.seg.nseg + k];
+      p.sumsq3[k] = t;
+      if (p.step) {
+        const int st = p.step[k] + 1;
+        p.step[k] = st;
+        p.sumsq3[p.seg.nseg + 2 * k] = 1.0 - pow(p.beta1, static_cast<double>(st));
+        p.sumsq3[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow(p.beta2, static_cast<double>(st)));
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *p.ticket = 0u;
+    *p.seq = seq;
+  }
+}
+
+struct VecParams {
+  Peers pe;
+  int rank, world;
+  double* __restrict__ out;        // mode 0: (n) sum over ranks; mode 1: (world, n) every rank's vector, rank order
+  int n;                           // doubles per rank (small: moments)
+  int gather;
+  unsigned* __restrict__ seq;
+};
+
+// one block: moments are a few hundred bytes
+__global__ void __launch_bounds__(kThreads) allreduce_f64_kernel(const VecParams p) {
+  const unsigned seq = *p.seq + 1u;
+  cross_rank_barrier(p.pe, p.rank, p.world, 0, seq);
+  for (int i = threadIdx.x; i < p.n; i += kThreads) {
+    if (p.gather) {
+      for (int r = 0; r < p.world; ++r) p.out[r * p.n + i] = ld_peer_f64(static_cast<const double*>(p.pe.data[r]) + i);
+    } else {
+      double v = 0.0;
+      for (int r = 0; r < p.world; ++r) v += ld_peer_f64(static_cast<const double*>(p.pe.data[r]) + i);
+      p.out[i] = v;
+    }
+  }
+  cross_rank_barrier(p.pe, p.rank, p.world, 1, seq);
+  if (threadIdx.x == 0) *p.seq = seq;
+}
+
+static bool fill_peers(Peers& pe, const void* const* data, void* const* flags, int world) {
+  if (world < 1 || world > kMaxWorld || !data || !flags) return false;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    pe.data[r] = r < world ? data[r] : nullptr;
+    pe.flags[r] = r < world ? static_cast<unsigned*>(flags[r]) : nullptr;
+    if (r < world && (!pe.data[r] || !pe.flags[r])) return false;
+  }
+  return true;
+}
+
+}  // namespace comm
+}  // namespace trl
+
+// ---- peer-mappable memory (the only allocations this library makes: communication buffers must be cudaMalloc blocks
+// of their own for cudaIpc; everything else stays in the caller's allocator) ------------------------------------------
+TRL_API int trl_comm_flag_bytes(void) { return trl::comm::kFlagWords * 4; }
+TRL_API int trl_comm_ipc_handle_bytes(void) { return static_cast<int>(sizeof(cudaIpcMemHandle_t)); }
+
+TRL_API int trl_comm_alloc(int64_t bytes, void** ptr_out) {
+  using namespace trl;
+  TRL_REQUIRE(bytes > 0 && ptr_out, "trl_comm_alloc: bad arguments");
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, static_cast<size_t>(bytes));
+  if (e == cudaSuccess) e = cudaMemset(p, 0, static_cast<size_t>(bytes));
+  if (e != cudaSuccess) { set_error("trl_comm_alloc: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  *ptr_out = p;
+  return TRL_OK;
+}
+
+TRL_API int trl_comm_free(void* ptr) {
+  using namespace trl;
+  cudaError_t e = cudaFree(ptr);
+  if (e != cudaSuccess) { set_error("trl_comm_free: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return TRL_OK;
+}
+
+TRL_API int trl_comm_ipc_get(void* ptr, void* handle_out) {
+  using namespace trl;
+  TRL_REQUIRE(ptr && handle_out, "trl_comm_ipc_get: null pointer");
+  cudaError_t e = cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle_out), ptr);
+  if (e != cudaSuccess) { set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return TRL_OK;
+}
+
+TRL_API int trl_comm_ipc_open(const void* handle, void** ptr_out) {
+  using namespace trl;
+  TRL_REQUIRE(handle && ptr_out, "trl_comm_ipc_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  cudaError_t e = cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return TRL_OK;
+}
+
+TRL_API int trl_comm_ipc_close(void* ptr) {
+  using namespace trl;
+  cudaError_t e = cudaIpcCloseMemHandle(ptr);
+  if (e != cudaSuccess) { set_error("cudaIpcCloseMemHandle: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return TRL_OK;
+}
+
+TRL_API int trl_comm_scratch_doubles(int nseg) { return trl::comm::kMaxBlocks * (nseg > 0 ? nseg : 1); }
+
+// out (n floats) = sum over ranks of peer_data[r] (rank order), sumsq3 as trl_grad_sumsq computes it for `out`; this
+// rank's operand (peer_data[rank]) is zeroed afterwards when zero_local.  peer_data / peer_flags: host arrays of `world`
+// device pointers (own entries included).  n % 4 == 0.  `seq`: device uint32 owned by the communicator (starts at 0).
+TRL_API int trl_allreduce_grad(const void* const* peer_data, void* const* peer_flags, int rank, int world, float* out,
+                               int64_t n, const int64_t* seg_begin_host, int nseg, unsigned active_mask,
+                               double* sumsq3_out, int* step_counts, double beta1, double beta2, double* scratch,
+                               unsigned* ticket, unsigned* seq, int zero_local, void* stream) {
+  using namespace trl;
+  using namespace trl::comm;
+  GradParams p;
+  TRL_REQUIRE(fill_peers(p.pe, peer_data, peer_flags, world), "trl_allreduce_grad: bad peer table (world %d)", world);
+  TRL_REQUIRE(rank >= 0 && rank < world, "trl_allreduce_grad: rank %d not in [0, %d)", rank, world);
+  TRL_REQUIRE(n > 0 && n % 4 == 0, "trl_allreduce_grad: n = %lld must be a positive multiple of 4", (long long)n);
+  TRL_REQUIRE(nseg >= 1 && nseg <= kMaxSeg && seg_begin_host, "trl_allreduce_grad: bad segment table");
+  TRL_REQUIRE(out && sumsq3_out && scratch && ticket && seq, "trl_allreduce_grad: null pointer");
+  for (int i = 0; i <= nseg; ++i) p.seg.begin[i] = seg_begin_host[i];
+  for (int i = nseg + 1; i <= kMaxSeg; ++i) p.seg.begin[i] = seg_begin_host[nseg];
+  for (int i = 0; i <= nseg; ++i) TRL_REQUIRE(p.seg.begin[i] % 4 == 0, "trl_allreduce_grad: segments must start on 16-byte boundaries");
+  p.seg.nseg = nseg;
+  p.rank = rank; p.world = world;
+  p.local = static_cast<float*>(const_cast<void*>(peer_data[rank]));
+  p.out = out; p.n = n; p.active_mask = active_mask; p.partial = scratch; p.sumsq3 = sumsq3_out; p.step = step_counts;
+  p.beta1 = beta1; p.beta2 = beta2; p.ticket = ticket; p.seq = seq; p.zero_local = zero_local;
+  long long blocks = ceil_div<long long>(n / 4, 2LL * kThreads);     // >= 2 float4 per thread
+  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  allreduce_grad_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("allreduce_grad_kernel");
+}
+
+// fp64 vectors of n elements per rank (moments): gather == 0: out (n) = sum over ranks; gather != 0: out (world, n).
+TRL_API int trl_allreduce_f64(const void* const* peer_data, void* const* peer_flags, int rank, int world, double* out,
+                              int n, int gather, unsigned* seq, void* stream) {
+  using namespace trl;
+  using namespace trl::comm;
+  VecParams p;
+  TRL_REQUIRE(fill_peers(p.pe, peer_data, peer_flags, world), "trl_allreduce_f64: bad peer table (world %d)", world);
+  TRL_REQUIRE(rank >= 0 && rank < world && n >= 1 && out && seq, "trl_allreduce_f64: bad arguments");
+  p.rank = rank; p.world = world; p.out = out; p.n = n; p.gather = gather; p.seq = seq;
+  allreduce_f64_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("allreduce_f64_kernel");
+}

@@ -135,8 +135,31 @@ class SynthVecEnv:
         self._host_mirror_ok = True
         # stats merge happens in-kernel; with a DataParallelContext the batch sums are all-reduced
         # over ranks first and merged by a separate launch (global statistics)
-        self.dist = None
+        self._dist = None
+        self._sums_red = None
         self.seed(0)
+
+    @property
+    def dist(self):
+        return self._dist
+
+    @dist.setter
+    def dist(self, ctx):
+        """Attach a DataParallelContext.  With PeerComm (distributed.py) the per-step batch sums move into a
+        peer-mapped region so that csrc/comm.cu sums them over ranks in one small kernel (no NCCL launch per step).
+        Must happen before the collector captures its step graph."""
+        self._dist = ctx
+        if ctx is not None and getattr(ctx, "active", False) and getattr(ctx, "peer", None) is not None:
+            local, _ = ctx.peer.region("obs_sums", 8 * self.batch_sums.numel(), torch.float64)
+            self.batch_sums = local[:self.batch_sums.numel()]
+            self.batch_sums.zero_()
+            self._sums_red = torch.zeros_like(self.batch_sums)
+
+    def _reduce_sums(self):
+        """Sum of `batch_sums` over ranks (identical on every rank)."""
+        if self._sums_red is not None:
+            return self._dist.peer.all_reduce_f64("obs_sums", self.batch_sums.numel(), self._sums_red)
+        return self._dist.all_reduce_sum_(self.batch_sums)
 
     # ------------------------------------------------------------------ reference API
     def train(self):
@@ -167,8 +190,8 @@ class SynthVecEnv:
             return self.obs_out
         if update and self.training:
             if self.dist is not None and self.dist.active:
-                sums = ops.obs_norm_moments(self.state, self.batch_sums)
-                self.dist.all_reduce_sum_(sums)
+                ops.obs_norm_moments(self.state, self.batch_sums)
+                sums = self._reduce_sums()
                 nrm = self._obs_normalizer
                 ops.obs_norm_merge(sums, self.total_envs, nrm._mean, nrm._var, nrm._count)
             else:
@@ -211,8 +234,7 @@ class SynthVecEnv:
                   int(max_episode_frames) if step_count is not None else (1 << 30),
                   1 if (update and not distributed) else 0, ops._stream())
         if update and distributed:
-            self.dist.all_reduce_sum_(self.batch_sums)
-            ops.obs_norm_merge(self.batch_sums, self.total_envs, nrm._mean, nrm._var, nrm._count)
+            ops.obs_norm_merge(self._reduce_sums(), self.total_envs, nrm._mean, nrm._var, nrm._count)
         if self.obs_norm:
             ops.obs_norm_filt(self.state, nrm._mean, nrm._var, nrm.clip, self.obs_out)
         return self.obs_out
@@ -229,7 +251,9 @@ class SynthVecEnv:
     def __deepcopy__(self, memo):
         new = SynthVecEnv.__new__(SynthVecEnv)
         for k, v in self.__dict__.items():
-            if torch.is_tensor(v):
+            if k == "_dist":
+                new.__dict__[k] = v                       # the job's communicator is shared, never copied
+            elif torch.is_tensor(v):
                 new.__dict__[k] = v.clone()
             else:
                 new.__dict__[k] = copy.deepcopy(v, memo)

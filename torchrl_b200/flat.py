@@ -85,12 +85,22 @@ class FlatAdam(FlatParams):
     """Adam over flat segments with per-segment lr / eps / max-norm, matching torch.optim.Adam +
     torch.nn.utils.clip_grad_norm_ applied per segment (the reference's per-network optimizers)."""
 
-    def __init__(self, segments, lrs, eps=1e-8, max_norms=None, betas=(0.9, 0.999), device=None):
+    def __init__(self, segments, lrs, eps=1e-8, max_norms=None, betas=(0.9, 0.999), device=None, dist=None):
         super().__init__(segments, device)
         n = len(self.segments)
         assert n <= 8
         self.nseg = n
-        self.grad = torch.zeros(self.total, dtype=F32, device=self.device)
+        # data parallel over PeerComm (distributed.py): the flat gradient lives in a peer-mapped region so that the
+        # fused all-reduce kernel reads it in place; `reduced` receives the sum over ranks
+        region = dist.grad_buffer(self.total) if dist is not None and getattr(dist, "active", False) else None
+        self._grad_region = region
+        if region is not None:
+            self.grad = region
+            self.grad.zero_()
+            self.reduced = torch.zeros(self.total, dtype=F32, device=self.device)
+            self._comm_scratch = torch.zeros(int(_lib.load().trl_comm_scratch_doubles(n)), dtype=F64, device=self.device)
+        else:
+            self.grad = torch.zeros(self.total, dtype=F32, device=self.device)
         self.exp_avg = torch.zeros(self.total, dtype=F32, device=self.device)
         self.exp_avg_sq = torch.zeros(self.total, dtype=F32, device=self.device)
         for p, o in zip(self.params, self.offsets):
@@ -124,14 +134,20 @@ class FlatAdam(FlatParams):
     def zero_grad(self):
         self.grad.zero_()
 
-    def step(self, active_mask=None, grad_scale=1.0, zero_grad=True):
-        """clip (per segment, global norm) + Adam + zero the gradient: two launches."""
+    def step(self, active_mask=None, grad_scale=1.0, zero_grad=True, reduced=False):
+        """clip (per segment, global norm) + Adam + zero the gradient: two launches.  reduced=True: the gradient
+        exchange kernel (distributed.reduce_grads) has already left the summed gradient in `self.reduced` together
+        with its norms / step counts and zeroed `self.grad`: only the Adam launch remains."""
         mask = self.all_mask if active_mask is None else int(active_mask)
         st = ops._stream()
-        _lib.call("trl_grad_sumsq", self.grad.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
-                  self.step_counts.data_ptr(), self.betas[0], self.betas[1], self._scratch.data_ptr(),
-                  self._ticket.data_ptr(), st)
-        _lib.call("trl_adam_step", self.data.data_ptr(), self.grad.data_ptr(), self.exp_avg.data_ptr(),
+        src = self.grad
+        if reduced:
+            src, zero_grad = self.reduced, False
+        else:
+            _lib.call("trl_grad_sumsq", self.grad.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
+                      self.step_counts.data_ptr(), self.betas[0], self.betas[1], self._scratch.data_ptr(),
+                      self._ticket.data_ptr(), st)
+        _lib.call("trl_adam_step", self.data.data_ptr(), src.data_ptr(), self.exp_avg.data_ptr(),
                   self.exp_avg_sq.data_ptr(), self._seg_c, self.nseg, mask, self.sumsq3.data_ptr(),
                   self.lr.data_ptr(), self._max_norm_c, self._eps_c, self.betas[0], self.betas[1],
                   float(grad_scale), int(bool(zero_grad)), self.hi.data_ptr(), self.lo.data_ptr(), st)
