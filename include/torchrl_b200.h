@@ -113,12 +113,20 @@ int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream);
 /* K12: the same statistics over the union of all ranks' minibatches: local raw moments [sum, sumsq, max, -min]
  * (fp64) -> one all-gather -> combine. */
 int trl_vec_moments(const float* x, int64_t n, double* moments4, void* stream);
+/* All minibatches of an epoch at once: moments4 (groups,4) = sum, sum of squares, max, -min of the rows
+ * idx[u*b .. (u+1)*b) of x; stats4 (groups,4) = mean, unbiased std, max, min from `world` ranks' moments. */
+int trl_row_group_moments(const float* x, const int64_t* idx, int groups, int b, int64_t row_elems,
+                          double* moments4, void* stream);
+int trl_group_stats_from_moments(const double* gathered, int world, int groups, double n_total, float* stats4,
+                                 void* stream);
 int trl_vec_stats_from_moments(const double* gathered, int world, double n_total, float* stats4, void* stream);
 
 /* ---- K8: PPO losses, value + gradient wrt the network outputs (algo/on_policy/ppo.py:41-122). */
 int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim);
 int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
-                       const float* old_logp, const float* advs, const float* adv_stats, int64_t B,
+                       const float* old_logp, const float* advs, const float* adv_stats,
+                       const int* adv_stats_pos /* device scalar: row (of 4 floats) of adv_stats to use; NULL: row 0 */,
+                       int64_t B,
                        int act_dim, int tanh_action, float clip_para, float entropy_coeff, float* g_mean,
                        float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
                        void* stream);

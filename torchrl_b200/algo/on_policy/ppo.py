@@ -94,6 +94,8 @@ class PPO(A2C):
             "log32": torch.zeros(U, 32, dtype=torch.float32, device=dev),
             "log64": torch.zeros(U, self.opt.sumsq3.numel(), dtype=torch.float64, device=dev),
             "scratch": ops.LossScratch(b * N, a, dev),
+            # advantage statistics of all U minibatches, computed once per epoch (mean, std, max, min per row)
+            "adv_table": torch.zeros(U, 4, dtype=torch.float32, device=dev),
             "keys": ["obs", "acts", "advs", "estimate_returns", "values", "old_logp"],
         }
         st["log_plan"] = ops.RowCopyPlan([st["info"], self.opt.sumsq3.view(1, -1)], [st["log32"], st["log64"]],
@@ -112,12 +114,7 @@ class PPO(A2C):
         st, rb = self._mb_state, self.replay_buffer
         batch = rb.gather_rows(st["perm"], st["keys"], pos_ptr=st["upd"], rows=st["b"])
         info = st["info"][0]
-        adv_stats = info[20:24]
         advs = batch["advs"].reshape(-1)
-        if self.dist is not None and self.dist.active:
-            self.dist.global_vec_stats(advs, adv_stats)      # moments span all ranks' envs (ppo.py:147)
-        else:
-            ops.vec_stats(advs, out=adv_stats)
         # critic
         v = self.vf(batch["obs"])
         g_v, _ = ops.ppo_critic_loss(v.reshape(-1), batch["estimate_returns"].reshape(-1),
@@ -127,8 +124,9 @@ class PPO(A2C):
         # actor
         mean, log_std = self._policy_outputs(self.pf, batch["obs"])
         g_mean, g_ls, _ = ops.ppo_actor_loss(mean, log_std, batch["acts"].reshape(mean.shape[0], -1),
-                                             batch["old_logp"].reshape(-1), advs, adv_stats, self.clip_para,
-                                             self.entropy_coeff, self.tanh_action, st["scratch"], info=info[0:16])
+                                             batch["old_logp"].reshape(-1), advs, st["adv_table"], self.clip_para,
+                                             self.entropy_coeff, self.tanh_action, st["scratch"], info=info[0:16],
+                                             stats_pos=st["upd"])
         torch.autograd.backward([mean, log_std], [g_mean, g_ls])
         # gradient exchange (multi-GPU) + clip + Adam + zero_grad
         scale, fused_norm = 1.0, False
@@ -153,10 +151,37 @@ class PPO(A2C):
             g.replay()
         self.training_update_num += 1
 
+    def _epoch_adv_stats(self):
+        """ppo.py:141-147 for ALL minibatches of the epoch at once: which time rows form minibatch u is known as
+        soon as the permutations are uploaded, so one launch reduces every minibatch's advantages to raw moments,
+        (data parallel) ONE exchange gathers the ranks' moments, one launch turns them into the (U,4) table the actor
+        loss indexes with the device counter.  Per minibatch this removes a reduction launch and, with several
+        ranks, an all-gather."""
+        st, rb = self._mb_state, self.replay_buffer
+        U, b = st["U"], st["b"]
+        dp = self.dist is not None and self.dist.active
+        W = self.dist.world_size if dp else 1
+        if "mom_all" not in st:
+            st["mom_all"] = torch.zeros(W, U, 4, dtype=torch.float64, device=self.device)
+            if dp and self.dist.peer is not None:
+                st["mom"] = self.dist.peer.region("adv_moments", 32 * U, torch.float64)[0][:4 * U].view(U, 4)
+            else:
+                st["mom"] = torch.zeros(U, 4, dtype=torch.float64, device=self.device) if dp else st["mom_all"][0]
+        advs = rb._advs.reshape(rb._advs.shape[0], -1)
+        ops.row_group_moments(advs, st["perm"], U, b, out=st["mom"])
+        if dp:
+            if self.dist.peer is not None:
+                self.dist.peer.all_reduce_f64("adv_moments", 4 * U, st["mom_all"], gather=True)
+            else:
+                import torch.distributed as tdist
+                tdist.all_gather_into_tensor(st["mom_all"].view(-1), st["mom"].view(-1))
+        ops.group_stats_from_moments(st["mom_all"], W, U, float(b * rb.env_nums * W), out=st["adv_table"])
+
     def _flush_infos(self, n_updates):
         """One D2H copy of the epoch's per-update scalars -> list of the reference's info dicts."""
         st = self._mb_state
         log32 = st["log32"][:n_updates].cpu().numpy()
+        log32[:, 20:24] = st["adv_table"][:n_updates].cpu().numpy()
         log64 = st["log64"][:n_updates].cpu().numpy()
         infos = []
         for u in range(n_updates):
@@ -194,6 +219,7 @@ class PPO(A2C):
             order = self.replay_buffer.epoch_order(self.shuffle)
             st["perm_host"][e * T:(e + 1) * T].copy_(torch.from_numpy(np.ascontiguousarray(order, dtype=np.int64)))
         st["perm"].copy_(st["perm_host"], non_blocking=True)
+        self._epoch_adv_stats()
         n = st["U"]
         for _ in range(n):
             self._run_minibatch()

@@ -137,6 +137,59 @@ __global__ void vec_stats_from_moments_kernel(const double* __restrict__ g, int 
   stats[3] = static_cast<float>(-nmn);
 }
 
+// raw moments of every minibatch of an epoch in ONE launch: CTA u reduces the b time rows idx[u*b .. (u+1)*b) of x
+// (rows of n floats) to out[4u ..] = sum, sum of squares, max, -min (fp64, fixed order) -- the minibatch membership is
+// known as soon as the epoch's row permutations are drawn (ppo.py:27-39, on_policy.py:72-91), so the advantage
+// statistics of ppo.py:141-147 need not be recomputed (nor all-reduced) per minibatch
+__global__ void __launch_bounds__(1024) row_group_moments_kernel(const float* __restrict__ x, const long long* __restrict__ idx,
+                                                                int b, long long n, double* __restrict__ out) {
+  __shared__ double sh_s[32], sh_q[32];
+  __shared__ float sh_mx[32], sh_mn[32];
+  double s = 0.0, q = 0.0;
+  float mx = -INFINITY, mn = INFINITY;
+  for (int k = 0; k < b; ++k) {
+    const float* row = x + idx[static_cast<long long>(blockIdx.x) * b + k] * n;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float v = row[i];
+      s += v; q += static_cast<double>(v) * v;
+      mx = fmaxf(mx, v); mn = fminf(mn, v);
+    }
+  }
+  s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { sh_s[wid] = s; sh_q[wid] = q; sh_mx[wid] = mx; sh_mn[wid] = mn; }
+  __syncthreads();
+  if (wid == 0) {
+    s = lane < nw ? sh_s[lane] : 0.0; q = lane < nw ? sh_q[lane] : 0.0;
+    mx = lane < nw ? sh_mx[lane] : -INFINITY; mn = lane < nw ? sh_mn[lane] : INFINITY;
+    s = warp_sum(s); q = warp_sum(q); mx = warp_max(mx); mn = warp_min(mn);
+    if (lane == 0) {
+      double* o = out + 4LL * blockIdx.x;
+      o[0] = s; o[1] = q; o[2] = mx; o[3] = -static_cast<double>(mn);
+    }
+  }
+}
+
+// stats[4u ..] = mean, unbiased std, max, min of group u from W ranks' raw moments g (W, U, 4), rank order
+__global__ void group_stats_from_moments_kernel(const double* __restrict__ g, int W, int U, double n_total,
+                                                float* __restrict__ stats) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= U) return;
+  double s = 0.0, q = 0.0, mx = -INFINITY, nmn = -INFINITY;
+  for (int r = 0; r < W; ++r) {
+    const double* m = g + (static_cast<long long>(r) * U + u) * 4;
+    s += m[0]; q += m[1];
+    mx = fmax(mx, m[2]); nmn = fmax(nmn, m[3]);
+  }
+  const double mean = s / n_total;
+  double var = (q - s * mean) / (n_total - 1.0);
+  if (var < 0.0) var = 0.0;
+  stats[4 * u] = static_cast<float>(mean);
+  stats[4 * u + 1] = static_cast<float>(sqrt(var));
+  stats[4 * u + 2] = static_cast<float>(mx);
+  stats[4 * u + 3] = static_cast<float>(-nmn);
+}
+
 }  // namespace trl
 
 static int launch_row_copy(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
@@ -205,4 +258,26 @@ TRL_API int trl_vec_stats_from_moments(const double* gathered, int world, double
   TRL_REQUIRE(gathered && stats4, "trl_vec_stats_from_moments: null pointer");
   vec_stats_from_moments_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(gathered, world, n_total, stats4);
   return check_launch("vec_stats_from_moments_kernel");
+}
+
+// moments4 (groups, 4) doubles: raw moments of x's rows idx[u*b .. (u+1)*b), one CTA per group
+TRL_API int trl_row_group_moments(const float* x, const int64_t* idx, int groups, int b, int64_t row_elems,
+                                  double* moments4, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(groups >= 1 && b >= 1 && row_elems >= 1, "trl_row_group_moments: bad sizes");
+  TRL_REQUIRE(x && idx && moments4, "trl_row_group_moments: null pointer");
+  row_group_moments_kernel<<<static_cast<unsigned>(groups), 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, reinterpret_cast<const long long*>(idx), b, row_elems, moments4);
+  return check_launch("row_group_moments_kernel");
+}
+
+// stats4 (groups, 4) floats = mean, unbiased std, max, min per group from `world` ranks' moments (world, groups, 4)
+TRL_API int trl_group_stats_from_moments(const double* gathered, int world, int groups, double n_total, float* stats4,
+                                         void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(world >= 1 && groups >= 1 && n_total >= 1, "trl_group_stats_from_moments: bad sizes");
+  TRL_REQUIRE(gathered && stats4, "trl_group_stats_from_moments: null pointer");
+  group_stats_from_moments_kernel<<<static_cast<unsigned>(ceil_div(groups, 128)), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      gathered, world, groups, n_total, stats4);
+  return check_launch("group_stats_from_moments_kernel");
 }

@@ -30,7 +30,8 @@ struct ActorParams {
   const float* __restrict__ actions;    // (B,a)
   const float* __restrict__ old_logp;   // (B)
   const float* __restrict__ advs;       // (B) raw advantages
-  const float* __restrict__ adv_stats;  // [mean, std] or nullptr (no normalisation)
+  const float* __restrict__ adv_stats;  // [mean, std, ..] rows of 4 floats, or nullptr (no normalisation)
+  const int* __restrict__ stats_pos;    // device scalar: which row of adv_stats (nullptr: row 0)
   float* __restrict__ g_mean;           // (B,a)
   float* __restrict__ g_log_std;        // (a) or (B,a)
   float* __restrict__ logp_out;         // (B) or nullptr
@@ -96,7 +97,10 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     ratio = expf(logp - oldlp);
     dkl = oldlp - logp;
     float adv = p.advs[b];
-    if (p.adv_stats) adv = (adv - p.adv_stats[0]) / (p.adv_stats[1] + 1e-5f);
+    if (p.adv_stats) {
+      const float* st = p.adv_stats + (p.stats_pos ? 4LL * (*p.stats_pos) : 0LL);
+      adv = (adv - st[0]) / (st[1] + 1e-5f);
+    }
     const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
     const float s1 = ratio * adv;
     const float s2 = fminf(fmaxf(ratio, lo), hi) * adv;
@@ -310,7 +314,8 @@ TRL_API int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim) {
 }
 
 TRL_API int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
-                               const float* old_logp, const float* advs, const float* adv_stats, int64_t B,
+                               const float* old_logp, const float* advs, const float* adv_stats,
+                               const int* adv_stats_pos, int64_t B,
                                int act_dim, int tanh_action, float clip_para, float entropy_coeff, float* g_mean,
                                float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
                                void* stream) {
@@ -320,7 +325,7 @@ TRL_API int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_s
   TRL_REQUIRE(ls_stride == 0 || ls_stride == act_dim, "trl_ppo_actor_loss: ls_stride must be 0 or act_dim");
   TRL_REQUIRE(mean && log_std && actions && old_logp && advs && g_mean && g_log_std && info16 && scratch && ticket,
               "trl_ppo_actor_loss: null pointer");
-  ActorParams p{mean, log_std, actions, old_logp, advs, adv_stats, g_mean, g_log_std, logp_out, info16, scratch,
+  ActorParams p{mean, log_std, actions, old_logp, advs, adv_stats, adv_stats_pos, g_mean, g_log_std, logp_out, info16, scratch,
                 ticket, B, act_dim, ls_stride, tanh_action, clip_para, entropy_coeff};
   ppo_actor_loss_kernel<<<static_cast<unsigned>(ceil_div<long long>(B, kLossThreads)), kLossThreads, 0,
                           static_cast<cudaStream_t>(stream)>>>(p);

@@ -225,7 +225,7 @@ class LossScratch:
 
 
 def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para, entropy_coeff, tanh_action,
-                   scratch, g_mean=None, g_log_std=None, info=None, logp_out=None):
+                   scratch, g_mean=None, g_log_std=None, info=None, logp_out=None, stats_pos=None):
     """PPO clipped-surrogate loss value, dL/dmean, dL/dlog_std and logged stats in one launch
     (/root/reference/torchrl/algo/on_policy/ppo.py:41-91)."""
     B, a = mean.shape
@@ -239,7 +239,8 @@ def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para,
         info = torch.zeros(16, dtype=F32, device=mean.device)
     _lib.call("trl_ppo_actor_loss", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
               _chk(actions, F32, "actions"), _chk(old_logp, F32, "old_logp"), _chk(advs, F32, "advs"),
-              _opt(adv_stats, F32, "adv_stats"), B, a, int(bool(tanh_action)), float(clip_para),
+              _opt(adv_stats, F32, "adv_stats"), _opt(stats_pos, I32, "stats_pos"), B, a, int(bool(tanh_action)),
+              float(clip_para),
               float(entropy_coeff), _chk(g_mean, F32, "g_mean"), _chk(g_log_std, F32, "g_log_std"),
               _opt(logp_out, F32, "logp_out"), _chk(info, F32, "info"), _chk(scratch.actor, F64, "scratch"),
               scratch.tickets[0:1].data_ptr(), _stream())
@@ -267,6 +268,25 @@ def gaussian_log_prob(mean, log_std, actions, tanh_action, out=None):
     ls_stride = 0 if log_std.dim() == 1 else a
     _lib.call("trl_gaussian_log_prob", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
               _chk(actions, F32, "actions"), B, a, int(bool(tanh_action)), _chk(out, F32, "logp"), _stream())
+    return out
+
+
+def row_group_moments(x, idx, groups, b, out=None):
+    """out (groups,4) f64 = sum, sum of squares, max, -min over the rows idx[u*b:(u+1)*b] of x (rows, n)."""
+    n = x.numel() // x.shape[0]
+    if out is None:
+        out = torch.empty(groups, 4, dtype=F64, device=x.device)
+    _lib.call("trl_row_group_moments", _chk(x, F32, "x"), _chk(idx, I64, "idx"), int(groups), int(b), n,
+              _chk(out, F64, "moments"), _stream())
+    return out
+
+
+def group_stats_from_moments(gathered, world, groups, n_total, out=None):
+    """out (groups,4) f32 = mean, unbiased std, max, min per group from (world, groups, 4) raw moments."""
+    if out is None:
+        out = torch.empty(groups, 4, dtype=F32, device=gathered.device)
+    _lib.call("trl_group_stats_from_moments", _chk(gathered, F64, "moments"), int(world), int(groups), float(n_total),
+              _chk(out, F32, "stats"), _stream())
     return out
 
 
