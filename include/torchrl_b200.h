@@ -123,6 +123,8 @@ int trl_vec_stats_from_moments(const double* gathered, int world, double n_total
 
 /* ---- K8: PPO losses, value + gradient wrt the network outputs (algo/on_policy/ppo.py:41-122). */
 int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim);
+/* old_logp == NULL: the plain policy-gradient loss of A2C, L = -mean(logp * adv) - c_ent * mean(ent)
+ * (algo/on_policy/a2c.py:66-70), same outputs. */
 int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
                        const float* old_logp, const float* advs, const float* adv_stats,
                        const int* adv_stats_pos /* device scalar: row (of 4 floats) of adv_stats to use; NULL: row 0 */,

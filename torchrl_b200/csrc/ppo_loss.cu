@@ -93,25 +93,31 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
       logp += l;
       if (p.ls_stride) { ls_s += ls; ls_q += ls * ls; ls_mx = fmaxf(ls_mx, ls); ls_mn = fminf(ls_mn, ls); }
     }
-    const float oldlp = p.old_logp[b];
-    ratio = expf(logp - oldlp);
-    dkl = oldlp - logp;
     float adv = p.advs[b];
     if (p.adv_stats) {
       const float* st = p.adv_stats + (p.stats_pos ? 4LL * (*p.stats_pos) : 0LL);
       adv = (adv - st[0]) / (st[1] + 1e-5f);
     }
-    const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
-    const float s1 = ratio * adv;
-    const float s2 = fminf(fmaxf(ratio, lo), hi) * adv;
-    Lb = -fminf(s2, s1);
-    // d(-min(s2,s1))/d ratio with torch's tie rule (equal -> split evenly)
-    const bool in_range = (ratio >= lo) && (ratio <= hi);
-    float dLdr;
-    if (s1 < s2) dLdr = -adv;
-    else if (s2 < s1) dLdr = in_range ? -adv : 0.f;
-    else dLdr = -0.5f * adv - (in_range ? 0.5f * adv : 0.f);
-    coef = dLdr * ratio * invB;  // dL/dlogp
+    if (p.old_logp) {
+      const float oldlp = p.old_logp[b];
+      ratio = expf(logp - oldlp);
+      dkl = oldlp - logp;
+      const float lo = 1.0f - p.clip, hi = 1.0f + p.clip;
+      const float s1 = ratio * adv;
+      const float s2 = fminf(fmaxf(ratio, lo), hi) * adv;
+      Lb = -fminf(s2, s1);
+      // d(-min(s2,s1))/d ratio with torch's tie rule (equal -> split evenly)
+      const bool in_range = (ratio >= lo) && (ratio <= hi);
+      float dLdr;
+      if (s1 < s2) dLdr = -adv;
+      else if (s2 < s1) dLdr = in_range ? -adv : 0.f;
+      else dLdr = -0.5f * adv - (in_range ? 0.5f * adv : 0.f);
+      coef = dLdr * ratio * invB;  // dL/dlogp
+    } else {
+      // plain policy gradient (A2C, /root/reference/torchrl/algo/on_policy/a2c.py:66-70): L_b = -logp_b * adv_b
+      Lb = -logp * adv;
+      coef = -adv * invB;
+    }
     if (p.logp_out) p.logp_out[b] = logp;
   }
 
@@ -323,7 +329,7 @@ TRL_API int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_s
   TRL_REQUIRE(B >= 1 && act_dim >= 1 && act_dim <= kMaxAct, "trl_ppo_actor_loss: bad sizes B=%lld a=%d (a<=%d)",
               (long long)B, act_dim, kMaxAct);
   TRL_REQUIRE(ls_stride == 0 || ls_stride == act_dim, "trl_ppo_actor_loss: ls_stride must be 0 or act_dim");
-  TRL_REQUIRE(mean && log_std && actions && old_logp && advs && g_mean && g_log_std && info16 && scratch && ticket,
+  TRL_REQUIRE(mean && log_std && actions && advs && g_mean && g_log_std && info16 && scratch && ticket,
               "trl_ppo_actor_loss: null pointer");
   ActorParams p{mean, log_std, actions, old_logp, advs, adv_stats, adv_stats_pos, g_mean, g_log_std, logp_out, info16, scratch,
                 ticket, B, act_dim, ls_stride, tanh_action, clip_para, entropy_coeff};

@@ -238,7 +238,7 @@ def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para,
     if info is None:
         info = torch.zeros(16, dtype=F32, device=mean.device)
     _lib.call("trl_ppo_actor_loss", _chk(mean, F32, "mean"), _chk(log_std, F32, "log_std"), ls_stride,
-              _chk(actions, F32, "actions"), _chk(old_logp, F32, "old_logp"), _chk(advs, F32, "advs"),
+              _chk(actions, F32, "actions"), _opt(old_logp, F32, "old_logp"), _chk(advs, F32, "advs"),
               _opt(adv_stats, F32, "adv_stats"), _opt(stats_pos, I32, "stats_pos"), B, a, int(bool(tanh_action)),
               float(clip_para),
               float(entropy_coeff), _chk(g_mean, F32, "g_mean"), _chk(g_log_std, F32, "g_log_std"),
