@@ -35,9 +35,10 @@ class A2C(OnRLAlgo):
         if optimizer_class is not optim.Adam:
             raise NotImplementedError("torchrl_b200 fuses clip+Adam in CUDA; only optim.Adam is supported")
         self.optimizer_class = optimizer_class
-        # segment 0 = policy, segment 1 = value net
-        self.opt = FlatAdam([self.pf, self.vf], lrs=[plr, vlr], eps=1e-5, max_norms=[0.5, 0.5], device=self.device,
-                            dist=self.dist)
+        # segment 0 = policy, segment 1 = value net (+ whatever a subclass optimises besides, e.g. V-MPO's duals)
+        extra = self._extra_opt_segments()
+        self.opt = FlatAdam([self.pf, self.vf] + [e[0] for e in extra], lrs=[plr, vlr] + [e[1] for e in extra], eps=1e-5,
+                            max_norms=[0.5, 0.5] + [e[2] for e in extra], device=self.device, dist=self.dist)
         self.pf_optimizer = SegmentOptimizer(self.opt, 0)
         self.vf_optimizer = SegmentOptimizer(self.opt, 1)
         self.entropy_coeff = entropy_coeff
@@ -50,6 +51,14 @@ class A2C(OnRLAlgo):
         self._last_infos = []
 
     # ------------------------------------------------------------------ what subclasses specialise
+    def _extra_opt_segments(self):
+        """[(parameter list, lr, max grad norm or 0)] optimised by the same fused step besides pf and vf."""
+        return []
+
+    def _step_mask(self):
+        """Bit mask of the optimizer segments that step in the minibatch loop (None: all)."""
+        return None
+
     def _passes(self):
         """Optimisation passes over the epoch's rollout (a2c: one; ppo: opt_epochs)."""
         return 1
@@ -71,6 +80,7 @@ class A2C(OnRLAlgo):
                                              batch["advs"].reshape(-1), st["adv_table"], 0.0, self.entropy_coeff,
                                              self.tanh_action, st["scratch"], info=info[0:16], stats_pos=st["upd"])
         torch.autograd.backward([mean, log_std], [g_mean, g_ls])
+        info[28:28 + log_std.numel()].copy_(log_std.detach())          # std/* (a2c.py:90-94) derive from it at flush
 
     def _pre_update(self):
         """Host-side work of an epoch before the minibatch loop (schedules, target copies)."""
@@ -145,12 +155,10 @@ class A2C(OnRLAlgo):
             info = st["info"][0]
             self._critic_step(batch, info)
             self._actor_step(batch, info)
-            a = rb._acts.shape[-1]
-            info[28:28 + a].copy_(self.pf.clamped_logstd().detach())       # std/* are derived from it at flush time
             scale, fused_norm = 1.0, False
             if self.dist is not None:
-                scale, fused_norm = self.dist.reduce_grads(self.opt)       # multi-GPU: exchange + norms in one kernel
-            self.opt.step(grad_scale=scale, reduced=fused_norm)
+                scale, fused_norm = self.dist.reduce_grads(self.opt, self._step_mask())   # exchange + norms, one kernel
+            self.opt.step(active_mask=self._step_mask(), grad_scale=scale, reduced=fused_norm)
             ops.ring_write(st["log_plan"], st["upd"])
             ops.counter_advance(None, st["upd"], st["U"])
 
