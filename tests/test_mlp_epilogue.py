@@ -160,6 +160,22 @@ def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
     x = torch.randn(M, inp, device="cuda", requires_grad=x_grad)
     x0 = x.detach().clone().requires_grad_(x_grad)
     w = torch.randn(M, out, device="cuda")
+    if act_name == "ReLU":
+        # relu'(y) = [y > 0] is discontinuous: a hidden unit whose pre-activation lies within round-off of zero can
+        # land on either side (the 3xTF32 tensor-core layer and the fp32 SIMT layer round differently), which changes
+        # that sample's whole back-propagated row.  Such samples are identified in fp64 (any hidden pre-activation
+        # with |z| < 1e-4, far above the 1e-6 round-off) and take no part in the backward pass (zero upstream
+        # gradient): for every remaining sample both routes see the same mask, so the SAME entry-wise round-off
+        # tolerances as for Tanh apply -- a wrong mask or scale in the fused kernels cannot hide.
+        with torch.no_grad():
+            fcs = [m for m in ref.modules() if isinstance(m, nn.Linear)]
+            h, risky = x.detach().double(), torch.zeros(M, dtype=torch.bool, device="cuda")
+            for fc in fcs[:-1]:
+                z = h @ fc.weight.double().t() + fc.bias.double()
+                risky |= (z.abs() < 1e-4).any(dim=1)
+                h = torch.relu(z)
+        assert risky.float().mean().item() < 0.2, "too many samples near a ReLU kink for a meaningful comparison"
+        w[risky] = 0.0
     assert fused._SKINNY                      # default route
     y1 = net(x)
     (y1 * w).sum().backward()
@@ -172,19 +188,9 @@ def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
         fused.set_matmul_mode("tc3")
         fused.set_skinny(True)
     torch.testing.assert_close(y1, y0, rtol=2e-5, atol=2e-6)
-    if act_name == "ReLU":
-        # relu'(y) = [y > 0] is discontinuous: a handful of the 4M hidden units sit within round-off of zero (the
-        # 3xTF32 tensor-core layer and the fp32 SIMT layer round differently) and switch side.  One switched unit
-        # changes that sample's whole back-propagated row, i.e. one of the M terms of EVERY entry of the earlier
-        # layers' weight gradients, so entry-wise tolerances at round-off level cannot hold.  A few rows out of
-        # M >= 1500 bound the relative Frobenius error by ~sqrt(flips / M) (a wrong mask or scale gives O(1)); the
-        # Tanh variants of this test hold the same kernels to round-off tolerances entry by entry.
-        def close(a, b, scale, name):
-            rel = ((a - b).norm() / (b.norm() + 1e-30)).item()
-            assert rel < 3e-2, (name, rel)
-    else:
-        def close(a, b, scale, name):
-            torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=name)
+
+    def close(a, b, scale, name):
+        torch.testing.assert_close(a, b, rtol=1e-4, atol=2e-5 * scale, msg=name)
     if x_grad:
         close(x.grad, x0.grad, 0.5 * x0.grad.abs().max().item(), "x")
     for (n1, p1), (n0, p0) in zip(net.named_parameters(), ref.named_parameters()):
