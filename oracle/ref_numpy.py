@@ -256,9 +256,18 @@ def adam_step(p, g, m, v, step, lr, beta1=0.9, beta2=0.999, eps=1e-8):
 def per_sample(prio, size, u, beta):
     """Stratified proportional sampling of time rows + importance weights.
 
-    PARITY UNPINNED: the reference has no prioritised replay; this is the CPU
-    statement of the definition in torchrl_b200/csrc/prioritized.cu.  prio: (rows,) float32 priorities
-    (already ^alpha); u: (b,) uniforms in [0,1).  Returns (idx int64 (b,), weights float64 (b,))."""
+    PARITY UNPINNED against the reference (it has no prioritised replay).  What is restated here
+    is the PUBLISHED algorithm -- Schaul, Quan, Antonoglou, Silver, "Prioritized Experience Replay", ICLR 2016
+    (arXiv:1511.05952), proportional variant -- at this buffer's sampling granularity (one priority per time row):
+      * eq. (1): P(i) = p_i^alpha / sum_k p_k^alpha            (`prio` already holds p_i^alpha, see per_update)
+      * sec. 3.4: w_i = (N * P(i))^-beta, normalised by max_i w_i = (N * min_k P(k))^-beta
+      * appendix B.2.1: "to sample a minibatch of size k, the range [0, p_total] is divided equally into k ranges;
+        next, a value is uniformly sampled from each range": target_k = (k + u_k) / b * p_total, and the row whose
+        cumulative priority interval contains the target is retrieved (their sum-tree walk == searchsorted on the
+        inclusive prefix sum).
+    tests/test_per_oracle.py holds this function to those three statements (sampling frequencies, weight formula,
+    one draw per stratum).  prio: (rows,) float32; u: (b,) uniforms in [0,1).  Returns (idx int64 (b,), weights
+    float64 (b,))."""
     p = np.asarray(prio[:size], dtype=np.float64)
     pre = np.cumsum(p)
     total = pre[-1]
@@ -272,7 +281,9 @@ def per_sample(prio, size, u, beta):
 
 
 def per_update(prio, idx, td, alpha, eps, max_prio):
-    """prio[idx_k] = (mean_n |td[k,n]| + eps)^alpha; returns the new running maximum priority."""
+    """Schaul et al. 2016, Algorithm 1 line 12 with the proportional priority of sec. 3.3: p_i = |delta_i| + eps,
+    stored as p_i^alpha.  A sampled index is a time row of N transitions: its |delta| is the mean over the row's N
+    TD errors.  Returns the new running maximum priority (Algorithm 1 line 6: new transitions enter with max p)."""
     new = (np.abs(np.asarray(td, dtype=np.float64)).mean(axis=1).astype(np.float32) + np.float32(eps)) ** np.float32(alpha)
     prio[idx] = new
     return max(float(max_prio), float(new.max()))
