@@ -40,7 +40,7 @@ def test_oracle_env_through_gym_api():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env_id,N", [("SynthHalfCheetah-v0", 70), ("SynthAnt-v0", 33)])
+@pytest.mark.parametrize("env_id,N", [("SynthHalfCheetah-v0", 70), ("SynthAnt-v0", 33), ("SynthHalfCheetahTerm-v0", 70)])
 def test_reset_bit_exact_and_step_parity(env_id, N):
     import torch
     from torchrl_b200.env import get_vec_env

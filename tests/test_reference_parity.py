@@ -15,20 +15,26 @@ import pytest
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("max_frames", [999, 7])
-def test_ppo_epoch_matches_reference_port(max_frames):
+@pytest.mark.parametrize("max_frames,env_id,N,T", [(999, "SynthHalfCheetah-v0", 8, 16), (7, "SynthHalfCheetah-v0", 8, 16),
+                                                   (999, "SynthHalfCheetahTerm-v0", 64, 32)])
+def test_ppo_epoch_matches_reference_port(max_frames, env_id, N, T):
+    """Lock-step episodes, collector time-outs every 7 frames (bootstrap + quirk A.1), and the variant with
+    state-dependent early termination: episodes desynchronise, some envs reset on most steps, the extra V(next_obs)
+    forward of collector/on_policy.py:132-148 runs on every step."""
     import torch
     from oracle import ref_port
     from torchrl_b200.policies import set_noise_mode
     from tests.test_ppo_pipeline import _build
-    N, T, hidden, rows, oe, seed = 8, 16, (32, 32), 4, 2, 5
+    hidden, rows, oe, seed = (32, 32), 4, 2, 5
     keys = ("obs", "next_obs", "acts", "values", "rewards", "terminals", "time_limits")
     # ---- CPU oracle port ------------------------------------------------------------------
     torch.set_num_threads(4)
-    penv, pcol, pagent = ref_port.build_ppo(env_nums=N, horizon=T, hidden=hidden, batch_rows=rows, opt_epochs=oe,
-                                            seed=seed, max_episode_frames=max_frames)
+    penv, pcol, pagent = ref_port.build_ppo(env_id=env_id, env_nums=N, horizon=T, hidden=hidden, batch_rows=rows,
+                                            opt_epochs=oe, seed=seed, max_episode_frames=max_frames)
     pagent.current_epoch = 0
     p_out = pcol.train_one_epoch()
+    if env_id.endswith("Term-v0"):
+        assert pagent.buffer.data["terminals"].sum() >= 3, "the variant must actually terminate episodes early"
     roll = {k: pagent.buffer.data[k].copy() for k in keys}
     pagent.update_per_epoch()
     # ---- device product, reference noise --------------------------------------------------
@@ -36,7 +42,7 @@ def test_ppo_epoch_matches_reference_port(max_frames):
     try:
         for use_graph in (False, True):
             agent, col, buf, env = _build(N=N, T=T, hidden=hidden, use_graph=use_graph, seed=seed, opt_epochs=oe,
-                                          max_frames=max_frames, batch_rows=rows)
+                                          max_frames=max_frames, batch_rows=rows, env_id=env_id)
             agent.current_epoch = 0
             out = col.train_one_epoch()
             assert abs(out["train_epoch_reward"] - p_out["train_epoch_reward"]) < 1e-3

@@ -24,6 +24,11 @@ SPECS = {
     # id: (obs_dim, act_dim, termination threshold on |s'[1]|)
     "SynthHalfCheetah-v0": (17, 6, float("inf")),
     "SynthAnt-v0": (111, 8, 2.3),
+    # HalfCheetah-shaped with state-dependent early termination: |s'[1]| grows towards ~2.4 under this dynamics and
+    # crosses 2.2 after 15-30 steps depending on the start state and the actions, so every env runs episodes of its
+    # own length, ~5 % of the envs terminate on any step, and the collector's reset / bootstrap branch
+    # (/root/reference/torchrl/collector/on_policy.py:132-148) has work on every step
+    "SynthHalfCheetahTerm-v0": (17, 6, 2.2),
 }
 
 
