@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true",
+                    help="skip the secondary measurements (BASELINE configs[0], [2], [3] and the desynchronised-episode PPO)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="env worker processes of the CPU arm (0 = auto)")
     ap.add_argument("--cpu-budget-s", type=float, default=900.0,
                     help="wall-clock budget of the CPU arm; whole epochs are dropped (never shortened) beyond it")
@@ -422,6 +424,124 @@ def gae_in_step_time(agent, buf, iters=20):
     return s.elapsed_time(e) * 1e-3 / iters
 
 
+# ----------------------------------------------------------------------------------------- secondary numbers
+def _time_epochs(col, agent, epochs, warm=2):
+    """(ms collect, ms update) per epoch, CUDA events around whole phases."""
+    import torch
+    for e in range(warm):
+        agent.current_epoch = e
+        col.train_one_epoch()
+        agent.update_per_epoch()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    tc = tu = 0.0
+    for _ in range(epochs):
+        ev[0].record()
+        col.rollout_no_sync()
+        ev[1].record()
+        agent.update_per_epoch(flush_infos=False)
+        ev[2].record()
+        torch.cuda.synchronize()
+        tc += ev[0].elapsed_time(ev[1])
+        tu += ev[1].elapsed_time(ev[2])
+    return tc / epochs, tu / epochs
+
+
+def secondary_measurements(args, device):
+    """Driver-visible numbers for the BASELINE configs that are not the headline (each a few seconds):
+    configs[0] the reference's own CPU-runnable case (8 envs, 4 worker processes), configs[2] TwinSAC-Q on 1024
+    Ant-shaped envs with a 1M-transition ring, configs[3] QR-DQN + prioritised replay on 512 Atari-shaped envs, and
+    the headline PPO config on the env variant with desynchronised episodes (bootstrap branch active on every step)."""
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    import torchrl_b200.policies as policies
+    from torchrl_b200.algo import PPO, QRDQN, TwinSACQ
+    from torchrl_b200.collector import PixelVecCollector, VecCollector, VecOnPolicyCollector
+    from torchrl_b200.env import get_vec_env
+    from torchrl_b200.replay_buffers import BaseReplayBuffer, OnPolicyReplayBuffer, PrioritizedReplayBuffer
+    from torchrl_b200.utils import NullLogger
+    out = {}
+    # ---- configs[0]: the reference's CPU plumbing at its own size
+    try:
+        pipe = CpuPipeline(8, 4, min(8, os.cpu_count() or 1))
+        try:
+            pipe.epoch()
+            ts = [pipe.epoch()[0] for _ in range(3)]
+        finally:
+            pipe.close()
+        out["configs[0]"] = {"workload": "PPO SynthHalfCheetah-v0, 8 envs over 4 worker processes, horizon 128, MLP[256, 256], "
+                                         "CPU collector + CPU torch update (%s)" % pipe.kind,
+                             "env_steps_per_s": 8 * HORIZON * len(ts) / sum(ts), "epoch_s": ts, "kind": pipe.kind}
+    except Exception as e:                                          # noqa: BLE001
+        out["configs[0]"] = {"error": repr(e)[:200]}
+    # ---- headline config on the desynchronised-episode env
+    N = args.envs_per_gpu
+    env = get_vec_env("SynthHalfCheetahTerm-v0", {"reward_scale": 1, "obs_norm": True}, N, device=device)
+    ev_env = get_vec_env("SynthHalfCheetahTerm-v0", {"reward_scale": 1, "obs_norm": True}, N, device=device)
+    env.seed(0); torch.manual_seed(0); np.random.seed(0)
+    buf = OnPolicyReplayBuffer(env_nums=N, max_replay_buffer_size=HORIZON * N, time_limit_filter=True)
+    net = dict(hidden_shapes=list(HIDDEN), append_hidden_shapes=[], base_type=networks.MLPBase, activation_func=nn.Tanh)
+    pf = policies.GuassianContPolicyBasicBias(input_shape=OBS_DIM, output_shape=ACT_DIM, tanh_action=True, **net)
+    vf = networks.Net(input_shape=(OBS_DIM,), output_shape=1, **net)
+    col = VecOnPolicyCollector(vf, env=env, eval_env=ev_env, pf=pf, replay_buffer=buf, device=device,
+                               epoch_frames=HORIZON * N, max_episode_frames=999)
+    agent = PPO(pf=pf, vf=vf, plr=3e-4, vlr=3e-4, clip_para=0.2, opt_epochs=OPT_EPOCHS, tau=0.95, shuffle=True,
+                entropy_coeff=0.005, env=env, replay_buffer=buf, collector=col, logger=NullLogger(), discount=0.99,
+                num_epochs=488, batch_size=BATCH_ROWS * N, gae=True, device=device, save_dir=None)
+    tc, tu = _time_epochs(col, agent, 3, warm=3)
+    out["ppo_desynchronised_episodes"] = {
+        "workload": "configs[1] on SynthHalfCheetahTerm-v0 (state-dependent termination, ~5 % of the envs reset per step: "
+                    "V(next_obs) bootstrap forward on every collector step)",
+        "env_steps_per_s": HORIZON * N / (tc + tu) * 1e3, "ms_rollout": tc, "ms_update": tu}
+    del agent, col, buf, env, ev_env
+    torch.cuda.empty_cache()
+    # ---- configs[2]
+    N = 1024
+    env = get_vec_env("SynthAnt-v0", {"reward_scale": 1, "obs_norm": False}, N, device=device)
+    ev_env = get_vec_env("SynthAnt-v0", {"obs_norm": False}, N, device=device)
+    env.seed(0); torch.manual_seed(0); np.random.seed(0)
+    buf = BaseReplayBuffer(env_nums=N, max_replay_buffer_size=int(1e6))
+    net = dict(hidden_shapes=[256, 256], append_hidden_shapes=[], base_type=networks.MLPBase, activation_func=nn.ReLU)
+    pf = policies.GuassianContPolicy(input_shape=111, output_shape=16, tanh_action=True, **net)
+    qf1 = networks.QNet(input_shape=119, output_shape=1, **net)
+    qf2 = networks.QNet(input_shape=119, output_shape=1, **net)
+    col = VecCollector(env=env, eval_env=ev_env, pf=pf, replay_buffer=buf, device=device, epoch_frames=64 * N,
+                       max_episode_frames=999)
+    agent = TwinSACQ(pf=pf, qf1=qf1, qf2=qf2, plr=3e-4, qlr=3e-4, policy_std_reg_weight=0, policy_mean_reg_weight=0,
+                     env=env, replay_buffer=buf, collector=col, logger=NullLogger(), discount=0.99, batch_size=4 * N,
+                     device=device, save_dir=None, tau=0.005, opt_times=64, num_epochs=10)
+    tc, tu = _time_epochs(col, agent, 3)
+    out["configs[2]"] = {"workload": "TwinSAC-Q, 1024 SynthAnt envs (obs 111, act 8), 1M-transition ring, batch 4096, MLP[256, 256]",
+                         "collect_env_steps_per_s": 64 * N / tc * 1e3, "updates_per_s": 64 / tu * 1e3,
+                         "env_steps_per_s_at_1_update_per_step": 64 * N / (tc + tu) * 1e3}
+    del agent, col, buf, env, ev_env
+    torch.cuda.empty_cache()
+    # ---- configs[3]
+    N, Q = 512, 200
+    env = get_vec_env("SynthAtari-v0", {}, N, device=device)
+    ev_env = get_vec_env("SynthAtari-v0", {}, N, device=device)
+    env.seed(0); torch.manual_seed(0); np.random.seed(0)
+    buf = PrioritizedReplayBuffer(env_nums=N, max_replay_buffer_size=100 * N)
+    qf = networks.Net(input_shape=(4, 84, 84), output_shape=6 * Q,
+                      hidden_shapes=[[16, [8, 8], [4, 4], [0, 0]], [32, [4, 4], [2, 2], [0, 0]], [64, [3, 3], [1, 1], [0, 0]]],
+                      append_hidden_shapes=[512], base_type=networks.CNNBase, activation_func=nn.ReLU)
+    pf = policies.EpsilonGreedyQRDQNDiscretePolicy(quantile_num=Q, qf=qf, start_epsilon=0.1, end_epsilon=0.1,
+                                                   decay_frames=1000000, action_shape=6)
+    col = PixelVecCollector(env=env, eval_env=ev_env, pf=pf, replay_buffer=buf, device=device, epoch_frames=32 * N,
+                            max_episode_frames=50000)
+    agent = QRDQN(quantile_num=Q, qf=qf, pf=pf, qlr=5e-5, optimizer_info={"eps": 0.0003125}, env=env, replay_buffer=buf,
+                  collector=col, logger=NullLogger(), discount=0.99, batch_size=2 * N, device=device, save_dir=None,
+                  opt_times=16, use_soft_update=False, target_hard_update_period=10000, num_epochs=10)
+    tc, tu = _time_epochs(col, agent, 3)
+    out["configs[3]"] = {"workload": "QR-DQN (200 quantiles) + prioritised replay, 512 SynthAtari envs (4x84x84 uint8), batch 1024",
+                         "collect_env_steps_per_s": 32 * N / tc * 1e3, "updates_per_s": 16 / tu * 1e3}
+    del agent, col, buf, env, ev_env
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     from torchrl_b200 import _lib
@@ -533,6 +653,13 @@ def run_ours(args):
                                                     "times warm epochs)",
                         "detail": {"epoch_s": dt, "collect_s": tc, "update_s": tu}}
 
+    secondary = None
+    if ctx.rank == 0 and args.gpus == 1 and not args.skip_secondary:
+        try:
+            secondary = secondary_measurements(args, device)
+        except Exception as e:                                      # noqa: BLE001 -- never lose the headline line
+            secondary = {"error": repr(e)[:300]}
+
     if ctx.rank == 0:
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": ctx.world_size,
@@ -556,6 +683,8 @@ def run_ours(args):
             line["roofline"] = roofline
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
+        if secondary is not None:
+            line["secondary"] = secondary
         print(json.dumps(line), flush=True)
     # teardown: drop the captured graphs (they hold NCCL work) before leaving; with several ranks exit
     # hard after a final barrier -- destroy_process_group() was observed to hang for minutes when
