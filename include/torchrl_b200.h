@@ -201,6 +201,18 @@ int trl_per_update(float* prio, const int64_t* idx, const float* td, int b, int 
                    float* max_prio, void* stream);
 int trl_per_insert(float* prio, const int* row_ptr, const float* max_prio, void* stream);
 
+/* ---- frame-de-duplicated pixel replay (csrc/frames.cu): the device layout of LazyFrames + MemoryEfficientReplayBuffer
+ * (env/atari_wrapper.py:142-168, replay_buffers/memory_efficient_replay_buffer.py:5-33).  The ring keeps the newest
+ * frame of obs and of next_obs per (row, env) + an age byte; stacks are rebuilt (as float32 * scale) at gather time. */
+int trl_frame_ring_write(const uint8_t* stack, uint8_t* ring, uint8_t* age_ring, const int* elapsed, uint8_t* hist,
+                         int* hist_count, const int* top, const int* size, int64_t N, int C, int64_t F, int T, int frame,
+                         void* stream);
+int trl_frame_hist_advance(int* hist_count, const int* size, int T, void* stream);
+int trl_frame_stack_gather(const uint8_t* obs_last, const uint8_t* next_last, const uint8_t* age, const uint8_t* hist,
+                           const int* hist_count, const int64_t* idx, const int* pos, int rows, const int* top,
+                           const int* size, int64_t N, int C, int64_t F, int T, float scale, float* out_obs,
+                           float* out_next, void* stream);
+
 /* ---- K12: one-shot all-reduce over NVLink peer memory (csrc/comm.cu; no reference counterpart).
  * Communication buffers are cudaMalloc blocks of their own (cudaIpc needs that): the ONLY allocations this library
  * makes.  peer_data / peer_flags: host arrays of `world` device pointers, entry r = rank r's operand buffer / flag

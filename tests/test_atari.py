@@ -58,7 +58,7 @@ def test_atari_env_bit_exact_vs_oracle():
     np.testing.assert_allclose(f.cpu().numpy(), stack.astype(np.float32) / 255.0, rtol=1e-6)
 
 
-def _build_pixel(kind, N=16, rows=24, use_graph=True, prioritized=False):
+def _build_pixel(kind, N=16, rows=24, use_graph=True, prioritized=False, dedup=False, max_frames=30):
     import torch
     import torch.nn as nn
     import torchrl_b200.networks as networks
@@ -66,14 +66,15 @@ def _build_pixel(kind, N=16, rows=24, use_graph=True, prioritized=False):
     from torchrl_b200.algo import DQN, QRDQN
     from torchrl_b200.collector import PixelVecCollector
     from torchrl_b200.env import get_vec_env
-    from torchrl_b200.replay_buffers import BaseReplayBuffer, PrioritizedReplayBuffer
+    from torchrl_b200.replay_buffers import BaseReplayBuffer, MemoryEfficientReplayBuffer, PrioritizedReplayBuffer
     from torchrl_b200.utils import NullLogger
     dev = torch.device("cuda:0")
     env = get_vec_env("SynthAtari-v0", {}, N)
     eval_env = get_vec_env("SynthAtari-v0", {}, N)
     env.seed(0); torch.manual_seed(0); np.random.seed(0)
     Q = 11 if kind == "qrdqn" else 1
-    buf = (PrioritizedReplayBuffer if prioritized else BaseReplayBuffer)(env_nums=N, max_replay_buffer_size=rows * N)
+    cls = MemoryEfficientReplayBuffer if dedup else (PrioritizedReplayBuffer if prioritized else BaseReplayBuffer)
+    buf = cls(env_nums=N, max_replay_buffer_size=rows * N)
     qf = networks.Net(input_shape=(4, 84, 84), output_shape=6 * Q,
                       hidden_shapes=[[16, [8, 8], [4, 4], [0, 0]], [32, [4, 4], [2, 2], [0, 0]]],
                       append_hidden_shapes=[64], base_type=networks.CNNBase, activation_func=nn.ReLU)
@@ -84,7 +85,7 @@ def _build_pixel(kind, N=16, rows=24, use_graph=True, prioritized=False):
         pf = policies.EpsilonGreedyDQNDiscretePolicy(qf=qf, start_epsilon=0.5, end_epsilon=0.1, decay_frames=100,
                                                      action_shape=6)
     col = PixelVecCollector(env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device=dev, epoch_frames=8 * N,
-                            max_episode_frames=30, use_cuda_graph=use_graph)
+                            max_episode_frames=max_frames, use_cuda_graph=use_graph)
     common = dict(qf=qf, pf=pf, qlr=1e-3, optimizer_info={"eps": 1e-4}, env=env, replay_buffer=buf, collector=col,
                   logger=NullLogger(), discount=0.99, batch_size=4 * N, device=dev, save_dir=None, opt_times=4,
                   use_soft_update=False, target_hard_update_period=3, pretrain_epochs=1, num_epochs=2,
@@ -134,3 +135,50 @@ def test_qrdqn_with_prioritized_replay_on_pixels():
     agent.update_per_epoch()                                 # prioritised path: sample, weighted loss, new priorities
     assert len(agent._last_infos) == 4 and all(np.isfinite(i["Training/qf_loss"]) for i in agent._last_infos)
     assert not torch.equal(before, buf._priorities) and float(buf._priorities[:16].min()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_frame_deduplicated_ring_reconstructs_every_stack_exactly(use_graph):
+    """MemoryEfficientReplayBuffer (one frame of obs + one of next_obs per row, csrc/frames.cu) against the full-stack
+    ring filled by an identical run: after the ring has wrapped several times, EVERY row -- including the oldest ones,
+    whose older frames the ring has overwritten, and rows right after resets (collector time-outs every 5 frames and
+    missed balls) -- gathers to the same float32 stacks, bit for bit; the pixel storage is 4x smaller."""
+    import torch
+    runs = []
+    for dedup in (False, True):
+        agent, col, buf, env = _build_pixel("dqn", N=8, rows=10, use_graph=use_graph, dedup=dedup, max_frames=5)
+        for _ in range(37):                                  # 3.7 laps of the 10-row ring
+            col._step()
+        runs.append((buf, env))
+    (full, env0), (ded, env1) = runs
+    assert full._size == ded._size == 10 and full._top == ded._top == 7
+    idx = torch.arange(10, device="cuda")
+    a = full.gather_rows(idx, ["obs", "next_obs", "acts", "rewards", "terminals"])
+    b = ded.gather_rows(idx, ["obs", "next_obs", "acts", "rewards", "terminals"])
+    for k in ("acts", "rewards", "terminals"):
+        assert torch.equal(a[k], b[k]), k
+    for k in ("obs", "next_obs"):
+        assert a[k].dtype == torch.uint8 and b[k].dtype == torch.float32
+        want = env0.to_float(a[k].contiguous())
+        assert torch.equal(b[k], want), (k, (b[k] != want).float().mean().item())
+    assert int(ded._age.max()) == 3 and int(ded._age.min()) == 0      # both fresh and mid-episode rows are present
+    stacks = full._obs.numel() + full._next_obs.numel()
+    assert ded.stored_frame_bytes() < 0.27 * stacks * 10 / 10 + 8 * 3 * 7056 + 100
+    # device-position gather (what the captured update graphs use)
+    pos = torch.tensor([1], dtype=torch.int32, device="cuda")
+    table = torch.tensor([3, 4, 9, 0, 7, 2], dtype=torch.int64, device="cuda")
+    c = ded.gather_rows(table, ["obs"], pos_ptr=pos, rows=3)
+    want = env0.to_float(full.gather_rows(torch.tensor([0, 7, 2], device="cuda"), ["obs"])["obs"].contiguous())
+    assert torch.equal(c["obs"], want)
+
+
+@pytest.mark.gpu
+def test_dqn_trains_on_the_frame_deduplicated_ring():
+    agent, col, buf, env = _build_pixel("qrdqn", dedup=True)
+    agent.pretrain()
+    for epoch in range(2):
+        agent.current_epoch = epoch
+        col.train_one_epoch()
+        agent.update_per_epoch()
+        assert all(np.isfinite(i["Training/qf_loss"]) for i in agent._last_infos)

@@ -67,6 +67,9 @@ SIGNATURES = {
     "trl_gemm_tf32x3_nt": [vp, vp, vp, i64, i64, i32, vp, vp, i32, vp],
     "trl_gemm_tf32x3_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_transpose_f32": [vp, vp, i64, i32, vp],
+    "trl_frame_ring_write": [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i64, i32, i32, vp],
+    "trl_frame_hist_advance": [vp, vp, i32, vp],
+    "trl_frame_stack_gather": [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, i64, i32, i64, i32, f32, vp, vp, vp],
     "trl_comm_flag_bytes": [],
     "trl_comm_ipc_handle_bytes": [],
     "trl_comm_alloc": [i64, vp],

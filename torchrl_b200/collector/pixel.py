@@ -26,8 +26,16 @@ class PixelVecCollector(VecCollector):
         rb.device = rb.device or self.device
         assert rb.env_nums == N
         frame = tuple(self.env.observation_space.shape)
-        for k, shp, dt in (("obs", (N,) + frame, U8), ("next_obs", (N,) + frame, U8), ("acts", (N,), F32),
-                           ("rewards", (N, 1), F32), ("terminals", (N, 1), U8), ("time_limits", (N, 1), U8)):
+        self._dedup = bool(getattr(rb, "frame_dedup", False))
+        keys = [("acts", (N,), F32), ("rewards", (N, 1), F32), ("terminals", (N, 1), U8), ("time_limits", (N, 1), U8)]
+        if self._dedup:
+            # frame-de-duplicated ring (replay_buffers/memory_efficient.py): one frame of obs and one of next_obs per
+            # row instead of two C-frame stacks
+            if getattr(rb, "_stack", None) is None:
+                rb.allocate_frames(frame)
+        else:
+            keys = [("obs", (N,) + frame, U8), ("next_obs", (N,) + frame, U8)] + keys
+        for k, shp, dt in keys:
             if not hasattr(rb, "_" + k):
                 rb.allocate(k, shp, dt)
         rb._ensure_device()
@@ -39,8 +47,9 @@ class PixelVecCollector(VecCollector):
         self._d_rows = torch.zeros(self._T, N, 1, dtype=F32, device=dev)
         self._obs_f = torch.empty((N,) + frame, dtype=F32, device=dev)
         self._any_reset = torch.zeros(2, dtype=I32, device=dev)
-        self._plan_obs = ops.RowCopyPlan([self.env.obs.view(1, -1)], [rb._obs], [ops.row_bytes_of(rb._obs)])
-        self._plan_next = ops.RowCopyPlan([self.env.obs.view(1, -1)], [rb._next_obs], [ops.row_bytes_of(rb._next_obs)])
+        if not self._dedup:
+            self._plan_obs = ops.RowCopyPlan([self.env.obs.view(1, -1)], [rb._obs], [ops.row_bytes_of(rb._obs)])
+            self._plan_next = ops.RowCopyPlan([self.env.obs.view(1, -1)], [rb._next_obs], [ops.row_bytes_of(rb._next_obs)])
         self._eps_dev = torch.zeros(1, dtype=F32, device=dev)
         self._eps_host = torch.zeros(1, dtype=F32).pin_memory()
 
@@ -50,12 +59,18 @@ class PixelVecCollector(VecCollector):
     def _step_body(self, bootstrap):
         env, rb = self.env, self.replay_buffer
         with torch.no_grad():
-            ops.ring_write(self._plan_obs, rb._top_dev)
+            if self._dedup:
+                rb.write_obs(env.obs, env.elapsed)
+            else:
+                ops.ring_write(self._plan_obs, rb._top_dev)
             env.to_float(env.obs, self._obs_f)
             out = self.pf.explore(self._obs_f.unsqueeze(0), epsilon=self._eps_dev)
             self._act.copy_(out["action"].reshape(self._act.shape).to(F32))
             env.launch_step(self._act.reshape(-1))
-            ops.ring_write(self._plan_next, rb._top_dev)
+            if self._dedup:
+                rb.write_next_obs(env.obs)
+            else:
+                ops.ring_write(self._plan_next, rb._top_dev)
             _lib.call("trl_collect_finalize", self._d_ob.data_ptr(), self._d_ob.data_ptr(), self._d_state.data_ptr(),
                       self._act.data_ptr(), None, None, env.reward.data_ptr(), env.done.data_ptr(),
                       env.time_limit.data_ptr(), env.elapsed.data_ptr(), env.episode.data_ptr(), env.seeds.data_ptr(),
