@@ -10,6 +10,8 @@ The advantage statistics of every minibatch of the epoch are computed once up-fr
 syncs with the host inside the loop: the reference's 12 `.item()` calls per update (a2c.py:82-98) become one device
 log fetched per epoch.  The constructor re-homes pf and vf into one flat buffer (flat.FlatAdam).
 """
+import os
+
 import numpy as np
 import torch
 import torch.optim as optim
@@ -49,6 +51,8 @@ class A2C(OnRLAlgo):
         self._mb_eager_runs = 0
         self._mb_state = None
         self._last_infos = []
+        self.overlap_nets = os.environ.get("TORCHRL_B200_OVERLAP_NETS", "1") == "1"
+        self._side_stream = torch.cuda.Stream(device=self.device)
 
     # ------------------------------------------------------------------ what subclasses specialise
     def _extra_opt_segments(self):
@@ -153,8 +157,20 @@ class A2C(OnRLAlgo):
             st, rb = self._mb_state, self.replay_buffer
             batch = rb.gather_rows(st["perm"], st["keys"], pos_ptr=st["upd"], rows=st["b"])
             info = st["info"][0]
-            self._critic_step(batch, info)
-            self._actor_step(batch, info)
+            if self.overlap_nets:
+                # the critic and the actor branch share nothing but their (read-only) inputs: run them on two streams
+                # -- under capture this becomes two parallel branches of the graph -- so that their many
+                # latency-bound launches overlap instead of queueing behind one another
+                main = torch.cuda.current_stream(self.device)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._critic_step(batch, info)
+                self._actor_step(batch, info)
+                main.wait_stream(side)
+            else:
+                self._critic_step(batch, info)
+                self._actor_step(batch, info)
             scale, fused_norm = 1.0, False
             if self.dist is not None:
                 scale, fused_norm = self.dist.reduce_grads(self.opt, self._step_mask())   # exchange + norms, one kernel

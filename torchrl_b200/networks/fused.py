@@ -136,6 +136,12 @@ def split_tf32(t):
 _WGRAD_WS = {}
 
 
+def _stream_key():
+    """Scratch buffers (split-K slabs, reduction partials, tickets) are per CUDA stream: the critic and the actor
+    branch of a minibatch run concurrently on two streams (algo/on_policy/a2c.py) and must not share them."""
+    return torch.cuda.current_stream().cuda_stream
+
+
 def wgrad(gz, x, out=None):
     """dW = gz^T @ x  for gz (M,H), x (M,K): split-K batched GEMM + partial sum.
 
@@ -147,7 +153,7 @@ def wgrad(gz, x, out=None):
     K = x.shape[1]
     if _tc3_ok(M, K, M) and H % 128 == 0 and M % (32 * 64) == 0:
         # tcgen05 3xTF32, operands consumed M/N-major from their row-major storage, deterministic split-K
-        key = (H, str(gz.device))
+        key = (H, str(gz.device), _stream_key())
         ws = _WGRAD_WS.get(key)
         if ws is None:
             ws = _WGRAD_WS[key] = torch.empty(64 * H * 256, dtype=torch.float32, device=gz.device)
@@ -223,7 +229,7 @@ class _Workspace:
 
     @classmethod
     def get(cls, M, H, device):
-        key = (int(M), int(H), str(device))
+        key = (int(M), int(H), str(device), _stream_key())
         ws = cls.cache.get(key)
         if ws is None:
             n = int(_lib.load().trl_bias_act_bwd_scratch_floats(int(M), int(H)))
@@ -253,7 +259,7 @@ def _skinny_ok(x):
 
 
 def _tn_scratch(M, H, K, device):
-    key = (M, H, K, str(device))
+    key = (M, H, K, str(device), _stream_key())
     ws = _TN_WS.get(key)
     if ws is None:
         n = int(_lib.load().trl_skinny_tn_scratch_floats(M, H, K))
@@ -435,7 +441,7 @@ class _MLPTail(torch.autograd.Function):
         db2 = db2_out if db2_out is not None else torch.empty(H, dtype=torch.float32, device=dev)
         db3 = db3_out if db3_out is not None else torch.empty(N, dtype=torch.float32, device=dev)
         gz = torch.empty_like(y2)
-        key = ("dgrad_act", M, H, str(dev))
+        key = ("dgrad_act", M, H, str(dev), _stream_key())
         ws = _TN_WS.get(key)
         if ws is None:
             n = int(_lib.load().trl_skinny_dgrad_act_scratch_floats(M, H))
