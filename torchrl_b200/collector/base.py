@@ -78,6 +78,7 @@ class VecCollector:
         self._host_steps = np.zeros(N, dtype=np.int64)      # host mirror of current_step (host envs only)
         self._graphs = {}
         self._eager_steps = 0
+        self._side_stream = torch.cuda.Stream(device=self.device)
         self._alloc_buffer()
         self._ret_log = torch.full((self._T, N), float("nan"), dtype=F32, device=dev)
 
@@ -129,16 +130,28 @@ class VecCollector:
     def _step_body(self, bootstrap):
         with torch.no_grad():
             ob = self.current_ob
-            self._policy_action(ob)
+            side = None
             if self.on_policy:
-                self._value.copy_(self.vf(ob).reshape(-1))
+                # V(ob) is only needed by the finalize kernel: evaluate it on a second stream (a parallel branch of the
+                # captured step graph) while the policy forward, the sampling and the env step run on this one
+                main = torch.cuda.current_stream(self.device)
+                side = self._side_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    self._value.copy_(self.vf(ob).reshape(-1))
+            self._policy_action(ob)
             self.env.launch_step(self._act, self.current_step, self.max_episode_frames, self.replay_buffer._top_dev)
             if not getattr(self.env, "obs_norm", False):
                 self.env.obs_out.copy_(self.env.state)
             v_next = None
             if bootstrap:
+                if side is not None:
+                    main.wait_stream(side)          # one value net, one set of per-stream scratch: V(ob) first
+                    side = None
                 self._v_next.copy_(self.vf(self.env.obs_out).reshape(-1))
                 v_next = self._v_next
+            if side is not None:
+                main.wait_stream(side)
             self._finalize(v_next)
             if hasattr(self.replay_buffer, "mark_inserted"):
                 self.replay_buffer.mark_inserted()    # prioritised ring: the new row enters with the max priority
