@@ -164,7 +164,7 @@ def test_frame_deduplicated_ring_reconstructs_every_stack_exactly(use_graph):
         assert torch.equal(b[k], want), (k, (b[k] != want).float().mean().item())
     assert int(ded._age.max()) == 3 and int(ded._age.min()) == 0      # both fresh and mid-episode rows are present
     stacks = full._obs.numel() + full._next_obs.numel()
-    assert ded.stored_frame_bytes() < 0.27 * stacks * 10 / 10 + 8 * 3 * 7056 + 100
+    assert ded.stored_frame_bytes() < 0.35 * stacks          # 2 of 8 frames per row (+ a 3-frame history per env)
     # device-position gather (what the captured update graphs use)
     pos = torch.tensor([1], dtype=torch.int32, device="cuda")
     table = torch.tensor([3, 4, 9, 0, 7, 2], dtype=torch.int64, device="cuda")
