@@ -33,15 +33,18 @@ def main():
         col.train_one_epoch()
         agent.update_per_epoch()
     torch.cuda.synchronize()
-    torch.cuda.profiler.start()
-    for _ in range(a.steps):
-        col._step()
-    agent.process_epoch_samples()
-    agent._cache_old_logp()
-    for _ in range(a.minibatches):
-        agent._run_minibatch()
-    torch.cuda.synchronize()
-    torch.cuda.profiler.stop()
+    from torchrl_b200.networks import fused
+    with fused.presplit():                      # what the collector / agent epochs run under (pre-split weight planes)
+        torch.cuda.profiler.start()
+        for _ in range(a.steps):
+            col._step()
+        agent.process_epoch_samples()
+        agent._cache_old_logp()
+        agent._mb_state["upd"].zero_()
+        for _ in range(a.minibatches):
+            agent._run_minibatch()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
 
 
 if __name__ == "__main__":

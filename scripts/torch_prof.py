@@ -12,14 +12,15 @@ fused.set_matmul_mode(mode)
 ctx = DataParallelContext()
 class A:
     envs_per_gpu = bench.N_ENVS_PER_GPU
-    no_graph = False
+    no_graph = "--eager" in sys.argv
 agent, col, buf, env = bench.build_agent(A, ctx, ctx.device)
 for e in range(3):
     agent.current_epoch = e
     col.train_one_epoch(); agent.update_per_epoch()
 torch.cuda.synchronize()
 NMB = 8
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+agent._mb_state["upd"].zero_()
+with fused.presplit(), profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(NMB):
         agent._run_minibatch()
     torch.cuda.synchronize()
