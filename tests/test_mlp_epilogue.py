@@ -164,7 +164,7 @@ def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
         # relu'(y) = [y > 0] is discontinuous: a hidden unit whose pre-activation lies within round-off of zero can
         # land on either side (the 3xTF32 tensor-core layer and the fp32 SIMT layer round differently), which changes
         # that sample's whole back-propagated row.  Such samples are identified in fp64 (any hidden pre-activation
-        # with |z| < 1e-4, far above the 1e-6 round-off) and take no part in the backward pass (zero upstream
+        # with |z| < 1e-5 max|z|, several times the 2e-6 max|z| round-off of the 3xTF32 layer) and take no part in the backward pass (zero upstream
         # gradient): for every remaining sample both routes see the same mask, so the SAME entry-wise round-off
         # tolerances as for Tanh apply -- a wrong mask or scale in the fused kernels cannot hide.
         with torch.no_grad():
@@ -172,9 +172,9 @@ def test_skinny_layers_match_plain_torch(inp, out, M, x_grad, act_name):
             h, risky = x.detach().double(), torch.zeros(M, dtype=torch.bool, device="cuda")
             for fc in fcs[:-1]:
                 z = h @ fc.weight.double().t() + fc.bias.double()
-                risky |= (z.abs() < 1e-4).any(dim=1)
+                risky |= (z.abs() < max(2e-5, 1e-5 * z.abs().max().item())).any(dim=1)
                 h = torch.relu(z)
-        assert risky.float().mean().item() < 0.2, "too many samples near a ReLU kink for a meaningful comparison"
+        assert risky.float().mean().item() < 0.25, "too many samples near a ReLU kink for a meaningful comparison"
         w[risky] = 0.0
     assert fused._SKINNY                      # default route
     y1 = net(x)

@@ -26,9 +26,12 @@ class VecCollector:
 
     on_policy = False
 
-    def __init__(self, env, eval_env, pf, replay_buffer, epoch_frames, train_render=False, eval_episodes=1,
+    def __init__(self, env, eval_env=None, pf=None, replay_buffer=None, epoch_frames=None, train_render=False, eval_episodes=1,
                  eval_render=False, device='cpu', max_episode_frames=999, use_cuda_graph=True,
                  reference_quirks=True):
+        # `eval_env` is optional here (a copy of `env` is made): the reference's a2c / ddpg / dqn example scripts do not
+        # pass one although its BaseCollector requires it (collector/base.py:13)
+        assert pf is not None and replay_buffer is not None and epoch_frames is not None, "pf, replay_buffer, epoch_frames"
         self.pf = pf
         self.replay_buffer = replay_buffer
         self.env = env

@@ -172,7 +172,7 @@ class GuassianContPolicyBase:
         else:
             log_prob = (-((actions - mean) ** 2) / (2 * std ** 2) - torch.log(std) - _HALF_LOG_2PI).sum(-1, keepdim=True)
         ent = (0.5 + _HALF_LOG_2PI + torch.log(std)).sum(-1, keepdim=True)
-        return {"mean": mean, "dis": torch.distributions.Normal(mean, std), "log_std": log_std, "std": std,
+        return {"mean": mean, "dis": torch.distributions.Normal(mean, std, validate_args=False), "log_std": log_std, "std": std,
                 "log_prob": log_prob, "ent": ent}
 
 
