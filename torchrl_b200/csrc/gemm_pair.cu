@@ -24,13 +24,15 @@
 //   nn   : A (M x K) row-major, B (K x 256) row-major      dgrad    dX = G W
 //   tn   : A (K x M) row-major, B (K x 256) row-major      wgrad    dW = G^T X (split-K, deterministic reduce)
 //
-// Roles per CTA (192 threads, identical in both CTAs so that shared-memory offsets match):
+// Roles per CTA (576 threads, identical in both CTAs so that shared-memory offsets match):
 //   warp 0      TMA producer : this CTA's A tile and its half of B -> LOCAL full[s]
-//   warps 2..5  converters   : raw -> (hi in place, lo twin) for what is not pre-split, then one arrival per warp
+//   warps 2..17 converters   : raw -> (hi in place, lo twin) for what is not pre-split, then one arrival per warp
 //                              on the LEADER's conv[s] (remote arrive through mapa for rank 1)
-//   warp 1      MMA issuer   : rank 0 only: waits conv[s] (8 arrivals), issues 12 tcgen05.mma.cta_group::2 per
+//   warp 1      MMA issuer   : rank 0 only: waits conv[s] (32 arrivals), issues 12 tcgen05.mma.cta_group::2 per
 //                              stage, commits with multicast to empty[s] of BOTH CTAs; last commit -> tmem_full
-//   warps 2..5  epilogue     : each CTA drains its own 128 accumulator rows from its own TMEM
+//   warps 2..17 epilogue     : each CTA drains its own 128 accumulator rows from its own TMEM, four warps per lane
+//                              quadrant (measured: with one warp per quadrant the epilogue was latency-bound at 16 k
+//                              cycles with tanh, 8.5 k without -- more than the 12 k cycles of tensor work)
 #include "common.cuh"
 #include <cuda.h>
 
@@ -42,7 +44,9 @@ constexpr int kStages = 3;
 constexpr int kUmmaK = 8;                               // tf32: 32 bytes per MMA K-step
 constexpr int kTileBytes = kBM * kBK * 4;               // 16 KB: one (128 x 32) fp32 operand tile
 constexpr int kStageBytes = 4 * kTileBytes;             // 64 KB: A hi | A lo | B hi | B lo
-constexpr int kThreads = 192;
+constexpr int kWorkWarps = 16;                           // converter / epilogue warps: 4 per SM sub-partition
+constexpr int kWorkThreads = 32 * kWorkWarps;            // 512
+constexpr int kThreads = 64 + kWorkThreads;              // + TMA warp + MMA warp
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*bias*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -208,11 +212,8 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_rank();
   if (threadIdx.x == 0) TRL_TRACE(0);
-  float bias_r0 = 0.f, bias_r1 = 0.f;     // 128 epilogue threads x 2 floats, parked in shared memory after the set-up
-  if (warp >= 2 && p.bias) {
-    bias_r0 = p.bias[threadIdx.x - 64];
-    bias_r1 = p.bias[threadIdx.x + 64];
-  }
+  float bias_r0 = 0.f;                    // first 256 work threads: one bias value each, parked in smem after set-up
+  if (warp >= 2 && threadIdx.x - 64 < kBN && p.bias) bias_r0 = p.bias[threadIdx.x - 64];
   const int m_blk = blockIdx.x;           // this CTA's 128 output rows
   const int split = blockIdx.y;
   const int nkb = p.k_blocks_per_split;
@@ -227,7 +228,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       for (int s = 0; s < kStages; ++s) {
         mbar_init(&full[s], 1);
-        mbar_init(&conv[s], 8);           // 4 converter warps x 2 CTAs
+        mbar_init(&conv[s], 2 * kWorkWarps);   // every converter warp of both CTAs
         mbar_init(&empty[s], 1);
       }
       mbar_init(tmem_full, 1);
@@ -304,37 +305,39 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       umma_commit_multicast(tmem_full, 0b11);              // both accumulator halves are complete
     }
   } else {
-    // ------------------------------------------------------------------ converters (warps 2..5), then epilogue
-    const int ct = threadIdx.x - 64;                       // 0..127
-    bias_s[ct] = bias_r0;
-    bias_s[ct + 128] = bias_r1;
+    // ------------------------------------------------------------------ converters (warps 2..17), then epilogue
+    const int ct = threadIdx.x - 64;                       // 0..511
+    if (ct < kBN) bias_s[ct] = bias_r0;
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % kStages;
       const uint32_t ph = (kb / kStages) & 1;
       mbar_wait(&full[s], ph);
       if (ct == 0) TRL_TRACE(24 + kb);
       // all loads of this thread first (independent 16-byte accesses in flight), then convert and store
-      constexpr int kPer = kTileBytes / 16 / 128;          // 8 float4 per thread and tile
+      constexpr int kPer = kTileBytes / 16 / kWorkThreads; // 2 float4 per thread and tile
+      constexpr int kStep = kWorkThreads * 16;
       const uint32_t a_addr = smem_u32(a_hi(s)) + ct * 16, b_addr = smem_u32(b_hi(s)) + ct * 16;
-      float4 va[kPer];
+      float4 va[kPer], vb[kPer];
 #pragma unroll
-      for (int i = 0; i < kPer; ++i) va[i] = lds128(a_addr + i * 2048);
+      for (int i = 0; i < kPer; ++i) va[i] = lds128(a_addr + i * kStep);
+      if (!BSPLIT) {
+#pragma unroll
+        for (int i = 0; i < kPer; ++i) vb[i] = lds128(b_addr + i * kStep);
+      }
 #pragma unroll
       for (int i = 0; i < kPer; ++i) {
         float4 h, l;
         split4(va[i], h, l);
-        sts128(a_addr + i * 2048, h);
-        sts128(a_addr + kTileBytes + i * 2048, l);
+        sts128(a_addr + i * kStep, h);
+        sts128(a_addr + kTileBytes + i * kStep, l);
       }
       if (!BSPLIT) {
 #pragma unroll
-        for (int i = 0; i < kPer; ++i) va[i] = lds128(b_addr + i * 2048);
-#pragma unroll
         for (int i = 0; i < kPer; ++i) {
           float4 h, l;
-          split4(va[i], h, l);
-          sts128(b_addr + i * 2048, h);
-          sts128(b_addr + kTileBytes + i * 2048, l);
+          split4(vb[i], h, l);
+          sts128(b_addr + i * kStep, h);
+          sts128(b_addr + kTileBytes + i * kStep, l);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
@@ -347,7 +350,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     // epilogue: TMEM lane quadrant of this warp = warp % 4.  The operand stages are free now (tmem_full fires after
     // the last MMA of the pair has read them): this warp's 32 rows are parked there with a pitch of 260 floats.
-    asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps: bias_s is complete
+    asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");   // the epilogue warps: bias_s is complete
     mbar_wait(tmem_full, 0);
     if (ct == 0) TRL_TRACE(2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -355,9 +358,12 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // activation -> a warp-private (32 x 36) transposition buffer in the free operand stages -> global memory as
     // 128-byte row segments (one 16-byte piece per lane, 4 rows per store instruction: every 32-byte sector written
     // whole).  Stores of chunk c overlap the TMEM load and the MUFU work of chunk c + 1.
-    const int quad = warp & 3;
+    // 4 warps per TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..): each takes 2 of the 8 chunks, so
+    // that every SM sub-partition has 4 warps to hide the TMEM-load / MUFU / shared-memory latencies behind
+    const int quad = warp & 3, sub = (warp - 2) >> 2;
+    constexpr int kChunksPerWarp = (kBN / 32) / (kWorkWarps / 4);
     constexpr int kTP = 36;                                // floats: conflict-free for the row-wise STS.128 AND LDS.128
-    const uint32_t tbuf = smem_u32(smem) + static_cast<uint32_t>(quad * 32 * kTP * 4);
+    const uint32_t tbuf = smem_u32(smem) + static_cast<uint32_t>((warp - 2) * 32 * kTP * 4);
     const uint32_t my_row = tbuf + static_cast<uint32_t>(lane * kTP * 4);
     const uint32_t rd = tbuf + static_cast<uint32_t>(((lane >> 3) * kTP + (lane & 7) * 4) * 4);
     const uint32_t bias_addr = smem_u32(bias_s);
@@ -378,13 +384,15 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           "=r"(R[25]), "=r"(R[26]), "=r"(R[27]), "=r"(R[28]), "=r"(R[29]), "=r"(R[30]), "=r"(R[31])                   \
         : "r"(ADDR))
     uint32_t ra[32], rb[32];
-    TRL_TMEM_LD32(ra, taddr0);
+    const int c_first = sub * kChunksPerWarp;
+    TRL_TMEM_LD32(ra, taddr0 + static_cast<uint32_t>(c_first * 32));
 #pragma unroll
-    for (int c = 0; c < kBN / 32; ++c) {
+    for (int cc = 0; cc < kChunksPerWarp; ++cc) {
+      const int c = c_first + cc;
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      uint32_t (&cur)[32] = (c & 1) ? rb : ra;
-      uint32_t (&nxt)[32] = (c & 1) ? ra : rb;
-      if (c + 1 < kBN / 32) TRL_TMEM_LD32(nxt, taddr0 + static_cast<uint32_t>((c + 1) * 32));
+      uint32_t (&cur)[32] = (cc & 1) ? rb : ra;
+      uint32_t (&nxt)[32] = (cc & 1) ? ra : rb;
+      if (cc + 1 < kChunksPerWarp) TRL_TMEM_LD32(nxt, taddr0 + static_cast<uint32_t>((c + 1) * 32));
       __syncwarp();                                        // the previous chunk has been read out of the buffer
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -409,7 +417,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int i = 0; i < 8; ++i)
         if (4 * i + (lane >> 3) < nrows)
           *reinterpret_cast<float4*>(cbase + static_cast<long long>(4 * i) * kBN + c * 32) = q[i];
-      if (ct == 0) TRL_TRACE(120 + c);
+      if ((ct & 127) == 0 && lane == 0) TRL_TRACE(120 + c);
     }
 #undef TRL_TMEM_LD32
     if (ct == 0) TRL_TRACE(3);
