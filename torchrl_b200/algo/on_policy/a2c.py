@@ -74,7 +74,8 @@ class A2C(OnRLAlgo):
         v = self.vf(batch["obs"])
         g_v, _ = ops.ppo_critic_loss(v.reshape(-1), batch["estimate_returns"].reshape(-1), None, False, 0.0,
                                      self._mb_state["scratch"], info=info[16:17])
-        torch.autograd.backward([v], [g_v.reshape(v.shape)])
+        with fused.backward_fork():
+            torch.autograd.backward([v], [g_v.reshape(v.shape)])
         ops.vec_stats(v.detach().reshape(-1), out=info[24:28])          # v_pred/* (a2c.py:85-88)
 
     def _actor_step(self, batch, info):
@@ -83,7 +84,8 @@ class A2C(OnRLAlgo):
         g_mean, g_ls, _ = ops.ppo_actor_loss(mean, log_std, batch["acts"].reshape(mean.shape[0], -1), None,
                                              batch["advs"].reshape(-1), st["adv_table"], 0.0, self.entropy_coeff,
                                              self.tanh_action, st["scratch"], info=info[0:16], stats_pos=st["upd"])
-        torch.autograd.backward([mean, log_std], [g_mean, g_ls])
+        with fused.backward_fork():
+            torch.autograd.backward([mean, log_std], [g_mean, g_ls])
         info[28:28 + log_std.numel()].copy_(log_std.detach())          # std/* (a2c.py:90-94) derive from it at flush
 
     def _pre_update(self):

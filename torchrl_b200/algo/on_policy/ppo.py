@@ -53,7 +53,8 @@ class PPO(A2C):
         g_v, _ = ops.ppo_critic_loss(v.reshape(-1), batch["estimate_returns"].reshape(-1),
                                      batch["values"].reshape(-1), self.clipped_value_loss, self.clip_para,
                                      self._mb_state["scratch"], info=info[16:17])
-        torch.autograd.backward([v], [g_v.reshape(v.shape)])
+        with fused.backward_fork():
+            torch.autograd.backward([v], [g_v.reshape(v.shape)])
 
     def _actor_step(self, batch, info):
         st = self._mb_state
@@ -62,7 +63,8 @@ class PPO(A2C):
                                              batch["old_logp"].reshape(-1), batch["advs"].reshape(-1), st["adv_table"],
                                              self.clip_para, self.entropy_coeff, self.tanh_action, st["scratch"],
                                              info=info[0:16], stats_pos=st["upd"])
-        torch.autograd.backward([mean, log_std], [g_mean, g_ls])
+        with fused.backward_fork():
+            torch.autograd.backward([mean, log_std], [g_mean, g_ls])
 
     def _cache_old_logp(self):
         """log pi_old(a|s) for every stored transition, once per epoch (see module docstring)."""
@@ -123,12 +125,14 @@ class PPO(A2C):
         v = self.vf(obs)
         g_v, _ = ops.ppo_critic_loss(v.reshape(-1), rets.reshape(-1), old_v.reshape(-1), self.clipped_value_loss,
                                      self.clip_para, scratch, info=info32[16:17])
-        torch.autograd.backward([v], [g_v.reshape(v.shape)])
+        with fused.backward_fork():
+            torch.autograd.backward([v], [g_v.reshape(v.shape)])
         mean, log_std = self._policy_outputs(self.pf, obs)
         g_mean, g_ls, _ = ops.ppo_actor_loss(mean, log_std, acts, old_logp, advs.reshape(-1), adv_stats,
                                              self.clip_para, self.entropy_coeff, self.tanh_action, scratch,
                                              info=info32[0:16])
-        torch.autograd.backward([mean, log_std], [g_mean, g_ls])
+        with fused.backward_fork():
+            torch.autograd.backward([mean, log_std], [g_mean, g_ls])
         scale, fused_norm = 1.0, False
         if self.dist is not None:
             scale, fused_norm = self.dist.reduce_grads(self.opt)

@@ -189,6 +189,41 @@ def mm3(a_hi, a_lo, b_hi, b_lo):
 
 
 _DIRECT_GRAD = False
+_FORK = None
+_FORK_STREAMS = {}
+
+
+class backward_fork:
+    """Scope around ONE `torch.autograd.backward` call of an MLP with a fused tail: the weight-gradient work that nothing
+    downstream in that backward pass depends on (output-layer dW / db and the 256 x 256 wgrad GEMM) is issued on a
+    companion stream while the dgrad GEMM and the first-layer backward continue on the calling stream; the scope's
+    exit joins the two (under graph capture: a parallel branch).  Tensors the companion stream reads are kept alive
+    until the join.  Outside such a scope the backward is strictly sequential."""
+
+    def __enter__(self):
+        global _FORK
+        self.main = torch.cuda.current_stream()
+        key = self.main.cuda_stream
+        if key not in _FORK_STREAMS:
+            _FORK_STREAMS[key] = torch.cuda.Stream(device=self.main.device)
+        self.side = _FORK_STREAMS[key]
+        self.keep, self.used, self.prev = [], False, _FORK
+        _FORK = self
+        return self
+
+    def __exit__(self, *a):
+        global _FORK
+        _FORK = self.prev
+        if self.used:
+            self.main.wait_stream(self.side)
+        self.keep.clear()
+
+
+def _fork_here():
+    f = _FORK
+    if f is not None and torch.cuda.current_stream().cuda_stream == f.main.cuda_stream:
+        return f
+    return None
 
 
 class direct_grad:
@@ -449,9 +484,20 @@ class _MLPTail(torch.autograd.Function):
         _lib.call("trl_skinny_n_dgrad_act", g.data_ptr(), w3.data_ptr(), y2.data_ptr(), gz.data_ptr(), db2.data_ptr(),
                   M, H, N, ctx.act, ws.data_ptr(), ops._stream())
         _lib.add_launches(1)
-        dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)      # dW3 (N,H) = g^T y2, db3 = sum g
-        dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
-        dw2 = wgrad(gz, x, out=dw2_out)
+        fk = _fork_here()
+        if fk is not None and dw2_out is not None and dw3_out is not None:
+            # the two weight gradients feed nothing but the optimizer: companion stream (see backward_fork)
+            fk.side.wait_stream(fk.main)
+            with torch.cuda.stream(fk.side):
+                dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)
+                dw2 = wgrad(gz, x, out=dw2_out)
+            fk.keep += [gz, g, y2, x]
+            fk.used = True
+            dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
+        else:
+            dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)  # dW3 (N,H) = g^T y2, db3 = sum g
+            dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
+            dw2 = wgrad(gz, x, out=dw2_out)
         return (dx, None if dw2_out is not None else dw2, None if db2_out is not None else db2,
                 None if dw3_out is not None else dw3, None if db3_out is not None else db3, None)
 
