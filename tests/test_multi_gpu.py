@@ -19,6 +19,12 @@ def _run(algo, comm, port):
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "scripts", "dist_check.py"), algo],
                        capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    try:                                        # keep the ranks' full output for diagnosis
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "dist_check_%s_%s.txt" % (algo, comm)), "w") as f:
+            f.write(r.stdout + "\n==== stderr ====\n" + r.stderr)
+    except OSError:
+        pass
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     oks = [l for l in r.stdout.splitlines() if l.startswith("dist_check ok")]
     assert len(oks) == 2, r.stdout[-3000:]                       # eager and CUDA-graph passes

@@ -8,8 +8,8 @@
 //
 // One kernel does the exchange AND the reduction that follows it:
 //   * every rank keeps its operand in a buffer that all peers have mapped (cudaIpc handles, exchanged once);
-//   * block b of every rank raises flag[ready][b][rank] in all peers' flag pads (st.release.sys) and waits for the W
-//     flags in its own pad: "everybody's operand is complete";
+//   * block b of every rank raises flag[ready][b][rank] in all peers' flag pads and waits for the W flags in its
+//     own pad: "everybody's operand is complete";
 //   * each thread sums its float4 / double slice over the W peer buffers IN RANK ORDER (so every rank computes the
 //     bit-identical result -- parameters never drift apart, no broadcast needed), writes the sum to a local output
 //     buffer and, for the gradient, accumulates the per-segment sum of squares in fp64 (two-level, fixed order: the
@@ -30,12 +30,12 @@ constexpr int kThreads = 256;
 constexpr int kMaxSeg = 8;
 constexpr int kFlagWords = 2 * kMaxBlocks * kMaxWorld;    // [phase][block][source rank] uint32
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_flag(unsigned* p, unsigned v) {
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+__device__ __forceinline__ unsigned ld_flag(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
@@ -54,15 +54,22 @@ struct Peers {
   unsigned* flags[kMaxWorld];      // flag pad of every rank (kFlagWords uint32)
 };
 
-// all blocks of all ranks: raise my flag of `phase` in every pad, wait for every rank's flag in my pad
+// All blocks of all ranks: raise my flag of `phase` in every pad, wait for every rank's flag in my pad.
+// No fences and no release / acquire qualifiers (measured: `__threadfence_system` + st.release.sys + ld.acquire.sys
+// cost two MEMBAR.SYS per phase, ~14 us per collective on 2 GPUs -- slower than NCCL):
+//   * phase 0 publishes data written by EARLIER kernels of this stream: complete in this GPU's L2 -- the coherence
+//     point peers read through -- before this kernel started;
+//   * phase 1 publishes "my reads are done": every thread has consumed its loaded values (they were summed and
+//     stored) before the __syncthreads() that precedes the flag store;
+//   * flags and peer data are accessed with .volatile (strong, system-scope: never served from a stale L1 line);
+//     the bar.sync orders the polling threads' loads before the other threads' data loads.
 __device__ __forceinline__ void cross_rank_barrier(const Peers& pe, int rank, int world, int phase, unsigned seq) {
   const int slot = (phase * kMaxBlocks + blockIdx.x) * kMaxWorld;
   __syncthreads();                                     // every thread of this block is done with the previous stage
   if (threadIdx.x < world) {
-    __threadfence_system();
-    st_release_sys(pe.flags[threadIdx.x] + slot + rank, seq);
+    st_flag(pe.flags[threadIdx.x] + slot + rank, seq);
     const unsigned* mine = pe.flags[rank] + slot + threadIdx.x;
-    while (static_cast<int>(ld_acquire_sys(mine) - seq) < 0) { }
+    while (static_cast<int>(ld_flag(mine) - seq) < 0) { }
   }
   __syncthreads();
 }
