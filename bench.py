@@ -574,7 +574,7 @@ def run_ours(args):
 
     # one nvidia-smi poller for the whole job (rank 0's GPU), started now so that its start-up is over before
     # the timed region (see ClockSampler)
-    sampler = ClockSampler(ctx.local_rank if ctx.rank == 0 else None)
+    sampler = ClockSampler(ctx.local_rank if (ctx.rank == 0 and os.environ.get("BENCH_NO_CLOCKS") != "1") else None)
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         epoch(True)

@@ -103,6 +103,11 @@ def main():
     build = build_ppo if algo == "ppo" else build_sac
     epochs = 2 if algo == "ppo" else 3
     for use_graph in (False, True):
+        # SAC draws its reparameterisation noise inside the update: with the CPU reference generator that cannot be
+        # captured, so its CUDA-graph pass runs on the device Philox streams (one per rank) and checks what does not
+        # depend on the noise source: the ranks stay bit-identical
+        philox = (algo == "sac" and use_graph)
+        D.set_noise_mode("philox" if philox else "reference_cpu")
         D.draw_reference_noise = sliced
         agent, col, buf, env = build(n_local, first, N_TOTAL, dev, ctx, use_graph)
         run(agent, col, epochs, pretrain=(algo == "sac"))
@@ -110,7 +115,12 @@ def main():
         other = [torch.zeros_like(flat) for _ in range(2)]
         torch.distributed.all_gather(other, flat)
         assert torch.equal(other[0], other[1]), "ranks diverged"
-        if ctx.rank == 0:
+        assert bool(torch.isfinite(flat).all())
+        if philox:
+            if ctx.rank == 0:
+                print("dist_check ok (%s, graph=%s, comm=%s): ranks bit-identical after %d epochs (device noise)"
+                      % (algo, use_graph, "peer" if ctx.peer is not None else "nccl", epochs), flush=True)
+        elif ctx.rank == 0:
             D.draw_reference_noise = full_draw
             a1, c1, b1, e1 = build(N_TOTAL, 0, N_TOTAL, dev, None, use_graph)
             run(a1, c1, epochs, pretrain=(algo == "sac"))

@@ -219,8 +219,11 @@ class backward_fork:
         self.keep.clear()
 
 
+_FORK_ENABLED = os.environ.get("TORCHRL_B200_BWD_FORK", "1") == "1"
+
+
 def _fork_here():
-    f = _FORK
+    f = _FORK if _FORK_ENABLED else None
     if f is not None and torch.cuda.current_stream().cuda_stream == f.main.cuda_stream:
         return f
     return None
