@@ -70,28 +70,67 @@ def measured_peaks():
 
 # ----------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi poller (`-lms`) for SM clocks and throttle reasons.  It is STARTED BEFORE THE WARM-UP: the
-    start-up of nvidia-smi (NVML attaches every GPU of the box) was measured to stall CUDA launches once for
-    ~0.4 s in about one run out of three (value leg 199 ms/step instead of 118; 266 instead of 137 at 4 ranks),
-    which must not land inside the timed region.  Only the samples stamped inside [mark_begin, mark_end] count."""
+    """SM clocks and throttle reasons DURING the timed region, sampled through NVML from a thread of this process
+    (pynvml: nvmlDeviceGetClockInfo / nvmlDeviceGetCurrentClocksEventReasons, every 100 ms).
+
+    Round 1 polled with an `nvidia-smi -lms` child process; even when started before the warm-up it made the
+    device-timed leg bistable -- 88 vs 120-127 ms/step at 2 GPUs in one run out of three, never without the poller
+    (gpurun_out/bench_n2_{default,nofork,noclocks,...}.txt, round 2) -- because a stalled launch thread on one rank
+    stalls every rank at the next collective.  The in-process NVML queries take microseconds and spawn nothing; the
+    child-process poller remains only as a fallback when pynvml is missing."""
+    _REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
-        self.proc = None
         self.gpu = gpu_index
         self.t0 = self.t1 = None
+        self.samples = []                    # (time, sm_mhz, sm_max_mhz, reason mask)
+        self._stop = False
+        self._thread = None
+        self.proc = None
+        self.path = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.gpu])
+            except (ValueError, IndexError):
+                pass
+        return self.gpu
+
+    def _loop(self, nv, handle):
+        while not self._stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                self.samples.append((time.time(), float(sm), float(mx), mask))
+            except Exception:                               # noqa: BLE001 -- a failed query is a missing sample
+                pass
+            time.sleep(0.1)
 
     def start(self):
         if self.gpu is None:
             return
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self._thread = threading.Thread(target=self._loop, args=(nv, handle), daemon=True)
+            self._thread.start()
+            return
+        except Exception:                                   # noqa: BLE001
+            self._thread = None
+        try:
+            self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
+        except Exception:                                   # noqa: BLE001
             self.proc = None
 
     def mark_begin(self):
@@ -108,44 +147,54 @@ class ClockSampler:
         except ValueError:
             return None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
+    def _read_child(self):
+        """Samples of the fallback nvidia-smi child process -> self.samples."""
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
-        except Exception:
+        except Exception:                                   # noqa: BLE001
             self.proc.kill()
-        rows_in, rows_all = [], []
         try:
             for line in open(self.path):
                 f = [x.strip() for x in line.split(",")]
                 if len(f) < 10:
                     continue
                 try:
-                    row = (float(f[2]), float(f[3]), f[6:10])
+                    clk, cmax = float(f[2]), float(f[3])
                 except ValueError:
                     continue
-                rows_all.append(row)
-                ts = self._stamp(f[0])
-                if ts is not None and self.t0 is not None and self.t1 is not None and self.t0 <= ts <= self.t1 + 0.1:
-                    rows_in.append(row)
+                mask = 0
+                for (bit, _), val in zip(self._REASONS, f[6:10]):
+                    if val.lower().startswith("active"):
+                        mask |= bit
+                self.samples.append((self._stamp(f[0]) or 0.0, clk, cmax, mask))
         except OSError:
             pass
-        sm, mx, reasons = [], [], set()
-        for clk, cmax, flags in (rows_in or rows_all):     # no stamped sample inside the region: keep them all
-            sm.append(clk); mx.append(cmax)
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            sm.sort()
-            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
         try:
             os.unlink(self.path)
         except OSError:
             pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "how": None}
+        if self._thread is not None:
+            self._stop = True
+            self._thread.join(timeout=2)
+            out["how"] = "nvml thread, 100 ms"
+        elif self.proc is not None:
+            self._read_child()
+            out["how"] = "nvidia-smi -lms 200"
+        else:
+            return out
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.05]
+        rows = inside or self.samples                       # no stamped sample inside the region: keep them all
+        if rows:
+            sm = sorted(x[1] for x in rows)
+            mask = 0
+            for x in rows:
+                mask |= x[3]
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(x[2] for x in rows),
+                       reasons=sorted(name for bit, name in self._REASONS if mask & bit), samples=len(rows))
         return out
 
 
