@@ -124,13 +124,16 @@ int trl_vec_stats_from_moments(const double* gathered, int world, double n_total
 /* ---- K8: PPO losses, value + gradient wrt the network outputs (algo/on_policy/ppo.py:41-122). */
 int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim);
 /* old_logp == NULL: the plain policy-gradient loss of A2C, L = -mean(logp * adv) - c_ent * mean(ent)
- * (algo/on_policy/a2c.py:66-70), same outputs. */
+ * (algo/on_policy/a2c.py:66-70), same outputs.
+ * ls_min <= ls_max: log_std is the RAW parameter; torch.clamp(log_std, ls_min, ls_max) of
+ * GuassianContPolicyBasicBias.forward (policies/continuous_policy.py:173-188) is applied inside, and g_log_std is the
+ * gradient with respect to the raw parameter (zero where the clamp is active).  ls_min > ls_max: no clamp. */
 int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
                        const float* old_logp, const float* advs, const float* adv_stats,
                        const int* adv_stats_pos /* device scalar: row (of 4 floats) of adv_stats to use; NULL: row 0 */,
                        int64_t B,
-                       int act_dim, int tanh_action, float clip_para, float entropy_coeff, float* g_mean,
-                       float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
+                       int act_dim, int tanh_action, float clip_para, float entropy_coeff, float ls_min, float ls_max,
+                       float* g_mean, float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
                        void* stream);
 int trl_ppo_critic_loss(const float* values, const float* returns, const float* old_values, int64_t B,
                         int clipped, float clip_para, float* g_values, float* info1, double* scratch,

@@ -23,7 +23,7 @@ def test_header_symbols_exported(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.trl_abi_version() == 2
+    assert native_lib.trl_abi_version() == 3
     assert native_lib.trl_last_error() is not None
 
 

@@ -73,6 +73,37 @@ def test_ppo_actor_loss_and_grads(shared_ls, B):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("shared_ls", [True, False])
+def test_ppo_actor_loss_folds_the_log_std_clamp(shared_ls):
+    """ls_clamp=(lo, hi): the kernel takes the RAW log-std, applies torch.clamp itself and returns the gradient of the
+    raw parameter -- identical to clamping outside and back-propagating through torch.clamp
+    (GuassianContPolicyBasicBias.forward, continuous_policy.py:173-188)."""
+    import torch
+    from torchrl_b200 import ops
+    torch.manual_seed(3)
+    dev, B, a, lo, hi = "cuda", 3000, 6, -2.0, -1.0
+    mean = (0.5 * torch.randn(B, a)).to(dev)
+    raw = (0.8 * torch.randn(a if shared_ls else (B, a)) - 1.5).to(dev)       # some entries outside [lo, hi]
+    assert ((raw < lo) | (raw > hi)).any() and ((raw >= lo) & (raw <= hi)).any()
+    acts = torch.tanh(mean + torch.randn(B, a, device=dev) * 0.3)
+    advs = torch.randn(B, device=dev)
+    old_lp = torch.randn(B, device=dev) * 0.1 - 3.0
+    scratch = ops.LossScratch(B, a, dev)
+    stats = ops.vec_stats(advs)
+    ls_c = raw.clone().requires_grad_()
+    clamped = torch.clamp(ls_c, lo, hi)
+    g_mean0, g_ls0, info0 = ops.ppo_actor_loss(mean, clamped.detach().contiguous(), acts, old_lp, advs, stats, 0.2, 0.005,
+                                               True, scratch)
+    clamped.backward(g_ls0)
+    g_mean1, g_ls1, info1 = ops.ppo_actor_loss(mean, raw, acts, old_lp, advs, stats, 0.2, 0.005, True, scratch,
+                                               ls_clamp=(lo, hi))
+    assert torch.equal(g_mean0, g_mean1)
+    assert torch.equal(info0, info1)
+    assert torch.equal(g_ls1, ls_c.grad)
+    assert (g_ls1[(raw < lo) | (raw > hi)] == 0).all()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("clipped", [False, True])
 def test_ppo_critic_loss_and_grads(clipped):
     import torch

@@ -50,7 +50,7 @@ SIGNATURES = {
     "trl_row_group_moments": [vp, vp, i32, i32, i64, vp, vp],
     "trl_group_stats_from_moments": [vp, i32, i32, f64, vp, vp],
     "trl_ppo_actor_scratch_doubles": [i64, i32],
-    "trl_ppo_actor_loss": [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
+    "trl_ppo_actor_loss": [vp, vp, i32, vp, vp, vp, vp, vp, i64, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp],
     "trl_ppo_critic_loss": [vp, vp, vp, i64, i32, f32, vp, vp, vp, vp, vp],
     "trl_gaussian_log_prob": [vp, vp, i32, vp, i64, i32, i32, vp, vp],
     "trl_grad_sumsq_blocks": [i32],

@@ -80,13 +80,15 @@ class A2C(OnRLAlgo):
 
     def _actor_step(self, batch, info):
         st = self._mb_state
-        mean, log_std = self._policy_outputs(self.pf, batch["obs"])
-        g_mean, g_ls, _ = ops.ppo_actor_loss(mean, log_std, batch["acts"].reshape(mean.shape[0], -1), None,
-                                             batch["advs"].reshape(-1), st["adv_table"], 0.0, self.entropy_coeff,
-                                             self.tanh_action, st["scratch"], info=info[0:16], stats_pos=st["upd"])
+        mean, raw_ls, clamp, g_ls = self._raw_policy_outputs(self.pf, batch["obs"])
+        g_mean, _, _ = ops.ppo_actor_loss(mean, raw_ls.detach(), batch["acts"].reshape(mean.shape[0], -1), None,
+                                          batch["advs"].reshape(-1), st["adv_table"], 0.0, self.entropy_coeff,
+                                          self.tanh_action, st["scratch"], g_log_std=g_ls, info=info[0:16],
+                                          stats_pos=st["upd"], ls_clamp=clamp)
         with fused.backward_fork():
-            torch.autograd.backward([mean, log_std], [g_mean, g_ls])
-        info[28:28 + log_std.numel()].copy_(log_std.detach())          # std/* (a2c.py:90-94) derive from it at flush
+            torch.autograd.backward([mean], [g_mean])
+        # std/* (a2c.py:90-94) derive from the clamped log-std at flush
+        torch.clamp(raw_ls.detach(), clamp[0], clamp[1], out=info[28:28 + raw_ls.numel()])
 
     def _pre_update(self):
         """Host-side work of an epoch before the minibatch loop (schedules, target copies)."""
@@ -112,6 +114,17 @@ class A2C(OnRLAlgo):
         if not log_std.is_contiguous():
             log_std = log_std.contiguous()
         return mean, log_std
+
+    def _raw_policy_outputs(self, pf, obs):
+        """Device minibatch path (a shared log-std PARAMETER, _device_path_ok): the mean, the raw parameter, its clamp
+        range and the slice of the flat gradient buffer that belongs to it.  The loss kernel applies the policy's
+        torch.clamp itself and writes the parameter's gradient in place, which removes the clamp / exp / clamp-backward
+        / accumulate launches on six-element tensors from every minibatch."""
+        from ...policies.continuous_policy import LOG_SIG_MIN, LOG_SIG_MAX
+        mean = pf.mean_net(obs)
+        if not mean.is_contiguous():
+            mean = mean.contiguous()
+        return mean, pf.logstd, (LOG_SIG_MIN, LOG_SIG_MAX), pf.logstd.grad
 
     def _device_path_ok(self):
         """The fused minibatch loop needs a Gaussian policy with a shared log-std vector (GuassianContPolicyBasicBias)

@@ -58,13 +58,13 @@ class PPO(A2C):
 
     def _actor_step(self, batch, info):
         st = self._mb_state
-        mean, log_std = self._policy_outputs(self.pf, batch["obs"])
-        g_mean, g_ls, _ = ops.ppo_actor_loss(mean, log_std, batch["acts"].reshape(mean.shape[0], -1),
-                                             batch["old_logp"].reshape(-1), batch["advs"].reshape(-1), st["adv_table"],
-                                             self.clip_para, self.entropy_coeff, self.tanh_action, st["scratch"],
-                                             info=info[0:16], stats_pos=st["upd"])
+        mean, raw_ls, clamp, g_ls = self._raw_policy_outputs(self.pf, batch["obs"])
+        g_mean, _, _ = ops.ppo_actor_loss(mean, raw_ls.detach(), batch["acts"].reshape(mean.shape[0], -1),
+                                          batch["old_logp"].reshape(-1), batch["advs"].reshape(-1), st["adv_table"],
+                                          self.clip_para, self.entropy_coeff, self.tanh_action, st["scratch"],
+                                          g_log_std=g_ls, info=info[0:16], stats_pos=st["upd"], ls_clamp=clamp)
         with fused.backward_fork():
-            torch.autograd.backward([mean, log_std], [g_mean, g_ls])
+            torch.autograd.backward([mean], [g_mean])
 
     def _cache_old_logp(self):
         """log pi_old(a|s) for every stored transition, once per epoch (see module docstring)."""

@@ -26,7 +26,7 @@ int check_launch(const char* what) {
 
 TRL_API const char* trl_last_error(void) { return trl::g_err; }
 
-TRL_API int trl_abi_version(void) { return 2; }
+TRL_API int trl_abi_version(void) { return 3; }
 
 // Number of SMs / name of the device the calling thread is bound to (diagnostics).
 TRL_API int trl_device_info(int* sm_count, int* cc_major, int* cc_minor) {

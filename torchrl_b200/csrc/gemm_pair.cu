@@ -172,10 +172,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
 }
-__device__ __forceinline__ float tanh_mufu(float x) {      // 1 - 2 / (exp(2x) + 1), same as csrc/skinny.cu
-  x = fminf(fmaxf(x, -15.f), 15.f);
-  return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
-}
+__device__ __forceinline__ float tanh_mufu(float x) { return ::trl::tanh_ex2(x); }   // common.cuh, as csrc/skinny.cu
 
 struct Params {
   const float* __restrict__ bias;  // (256) added in the epilogue, or nullptr
@@ -433,26 +430,35 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   if (threadIdx.x == 0) TRL_TRACE(5);
 }
 
-// C[i] = sum_s P[s][i]   (fixed order: 4 interleaved partial sums per element combined pairwise)
-__global__ void __launch_bounds__(256) pair_splitk_reduce_kernel(const float* __restrict__ P, float* __restrict__ C,
+// C[i] = sum_s P[s][i]   (fixed order: 8 interleaved partial sums per element, combined as a balanced tree).  512
+// threads = 64 float4 elements x 8 groups; a group's loads are independent, eight of them in flight.
+__global__ void __launch_bounds__(512) pair_splitk_reduce_kernel(const float* __restrict__ P, float* __restrict__ C,
                                                                 long long mn, int splits) {
-  __shared__ float4 sh[4][64];
+  __shared__ float4 sh[8][64];
   const int o = threadIdx.x & 63, g = threadIdx.x >> 6;
   const long long i = (static_cast<long long>(blockIdx.x) * 64 + o) * 4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < mn) {
-#pragma unroll 4
-    for (int s = g; s < splits; s += 4) {
-      const float4 v = *reinterpret_cast<const float4*>(P + static_cast<long long>(s) * mn + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    const float* pi = P + i;
+    for (int s0 = g; s0 < splits; s0 += 64) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = (s0 + 8 * u < splits) ? __ldcg(reinterpret_cast<const float4*>(pi + static_cast<long long>(s0 + 8 * u) * mn))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
     }
   }
   sh[g][o] = acc;
   __syncthreads();
   if (g == 0 && i < mn) {
-    const float4 a = sh[0][o], b = sh[1][o], c = sh[2][o], d = sh[3][o];
-    *reinterpret_cast<float4*>(C + i) =
-        make_float4((a.x + b.x) + (c.x + d.x), (a.y + b.y) + (c.y + d.y), (a.z + b.z) + (c.z + d.z), (a.w + b.w) + (c.w + d.w));
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = sh[u][o];
+#define TRL_T3(c) (((t[0].c + t[1].c) + (t[2].c + t[3].c)) + ((t[4].c + t[5].c) + (t[6].c + t[7].c)))
+    *reinterpret_cast<float4*>(C + i) = make_float4(TRL_T3(x), TRL_T3(y), TRL_T3(z), TRL_T3(w));
+#undef TRL_T3
   }
 }
 
@@ -585,6 +591,6 @@ TRL_API int trl_gemm3_pair_tn(const float* A, const float* B, float* C, int64_t 
                                      "gemm3_pair_kernel<tn>");
   if (rc != TRL_OK || splits == 1) return rc;
   const long long mn = M * kBN;
-  pair_splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 64)), 256, 0, st>>>(workspace, C, mn, splits);
+  pair_splitk_reduce_kernel<<<static_cast<unsigned>(ceil_div<long long>(mn / 4, 64)), 512, 0, st>>>(workspace, C, mn, splits);
   return check_launch("pair_splitk_reduce_kernel");
 }

@@ -123,10 +123,7 @@ __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
 }
 
-__device__ __forceinline__ float tanh_mufu(float x) {      // 1 - 2 / (exp(2x) + 1), same as csrc/skinny.cu
-  x = fminf(fmaxf(x, -15.f), 15.f);
-  return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
-}
+__device__ __forceinline__ float tanh_mufu(float x) { return ::trl::tanh_ex2(x); }   // common.cuh, as csrc/skinny.cu
 
 struct GemmParams {
   const float* __restrict__ bias;  // (256) added in the epilogue, or nullptr

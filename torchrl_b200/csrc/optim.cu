@@ -70,8 +70,17 @@ __global__ void __launch_bounds__(kOptThreads) grad_sumsq_kernel(const SumsqPara
   if (threadIdx.x < p.seg.nseg) {
     const int k = threadIdx.x;
     if ((p.active_mask >> k) & 1u) {
+      // the partials are requested 16 at a time before they are added (same order as a plain loop, one L2 round
+      // trip instead of one per partial)
       double t = 0.0;
-      for (int i = 0; i < p.blocks_per_seg; ++i) t += p.partial[k * p.blocks_per_seg + i];
+      for (int i0 = 0; i0 < p.blocks_per_seg; i0 += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u)
+          v[u] = (i0 + u < p.blocks_per_seg) ? __ldcg(p.partial + k * p.blocks_per_seg + i0 + u) : 0.0;
+#pragma unroll
+        for (int u = 0; u < 16; ++u) t += v[u];
+      }
       p.out[k] = t;
       if (p.step) {
         const int st = p.step[k] + 1;

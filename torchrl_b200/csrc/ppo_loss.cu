@@ -41,7 +41,17 @@ struct ActorParams {
   long long B;
   int a, ls_stride, tanh_action;
   float clip, ent_coef;
+  float ls_min, ls_max;                 // log_std is clamped to [ls_min, ls_max] first (ls_min > ls_max: no clamp)
 };
+
+// torch.clamp(log_std, lo, hi) folded into the loss (GuassianContPolicyBasicBias.forward,
+// /root/reference/torchrl/policies/continuous_policy.py:173-188): value, and whether the gradient passes
+// (clamp's backward lets it through for lo <= x <= hi)
+__device__ __forceinline__ float clamped_ls(const ActorParams& p, float raw, bool* pass) {
+  if (p.ls_min > p.ls_max) { *pass = true; return raw; }
+  *pass = (raw >= p.ls_min) && (raw <= p.ls_max);
+  return fminf(fmaxf(raw, p.ls_min), p.ls_max);
+}
 
 __device__ __forceinline__ double block_reduce_sum(double v, double* sh) {
   v = warp_sum(v);
@@ -83,7 +93,8 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     for (int j = 0; j < a; ++j) {
       const float act = p.actions[b * a + j];
       const float mu = p.mean[b * a + j];
-      const float ls = p.log_std[(p.ls_stride ? b * p.ls_stride : 0) + j];
+      bool pass;
+      const float ls = clamped_ls(p, p.log_std[(p.ls_stride ? b * p.ls_stride : 0) + j], &pass);
       const float sd = expf(ls);
       // pre-tanh value recovered exactly as the reference does: log((1+a)/(1-a))/2
       const float z = p.tanh_action ? 0.5f * logf((1.0f + act) / (1.0f - act)) : act;
@@ -134,13 +145,14 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     if (ok) {
       const float act = p.actions[b * a + j];
       const float mu = p.mean[b * a + j];
-      const float ls = p.log_std[(p.ls_stride ? b * p.ls_stride : 0) + j];
+      bool pass;
+      const float ls = clamped_ls(p, p.log_std[(p.ls_stride ? b * p.ls_stride : 0) + j], &pass);
       const float sd = expf(ls);
       const float z = p.tanh_action ? 0.5f * logf((1.0f + act) / (1.0f - act)) : act;
       const float d = (z - mu) / sd;
       p.g_mean[b * a + j] = coef * (d / sd);          // dlogp/dmu = (z-mu)/sd^2
       gl = coef * (d * d - 1.0f);                     // dlogp/dls = (z-mu)^2/sd^2 - 1
-      if (p.ls_stride) p.g_log_std[b * a + j] = gl - p.ent_coef * invB;  // entropy: d ent_b/d ls = 1
+      if (p.ls_stride) p.g_log_std[b * a + j] = pass ? gl - p.ent_coef * invB : 0.f;  // entropy: d ent_b/d ls = 1
     }
     if (!p.ls_stride) {
       const double w = warp_sum(static_cast<double>(gl));
@@ -197,9 +209,16 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     const bool is_max = (k == 3 || k == 5 || k == 9), is_min = (k == 4 || k == 6 || k == 10);
     double acc = is_max ? -INFINITY : (is_min ? INFINITY : 0.0);
     if (k < K) {
-      for (int i = chunk; i < nb; i += 4) {
-        const double v = p.partial[static_cast<long long>(i) * K + k];
-        acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+      // eight partials are requested before the first is folded (same fold order as a plain loop; a dependent
+      // load per partial made this tail ~nb/4 L2 round trips long)
+      const double ident = acc;
+      for (int i = chunk; i < nb; i += 32) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          v[u] = (i + 4 * u < nb) ? __ldcg(p.partial + static_cast<long long>(i + 4 * u) * K + k) : ident;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = is_max ? fmax(acc, v[u]) : (is_min ? fmin(acc, v[u]) : acc + v[u]);
       }
     }
     sh_fin[chunk][k] = acc;
@@ -228,7 +247,8 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     } else {
       double s = 0.0, q = 0.0; ls_max = -INFINITY; ls_min = INFINITY;
       for (int j = 0; j < a; ++j) {
-        const double ls = p.log_std[j];
+        bool pass;
+        const double ls = clamped_ls(p, p.log_std[j], &pass);
         s += ls; q += ls * ls; ls_max = fmax(ls_max, ls); ls_min = fmin(ls_min, ls);
       }
       ls_mean = s / a;
@@ -252,7 +272,11 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     p.info[11] = static_cast<float>(ent_mean);
     p.info[12] = static_cast<float>(t[11] / Bn);
     if (!p.ls_stride)
-      for (int j = 0; j < a; ++j) p.g_log_std[j] = static_cast<float>(t[kActorFixed + j]) - p.ent_coef;
+      for (int j = 0; j < a; ++j) {
+        bool pass;
+        clamped_ls(p, p.log_std[j], &pass);
+        p.g_log_std[j] = pass ? static_cast<float>(t[kActorFixed + j]) - p.ent_coef : 0.f;
+      }
     *p.ticket = 0u;
   }
 }
@@ -305,11 +329,15 @@ __global__ void __launch_bounds__(kLossThreads) ppo_critic_loss_kernel(const Cri
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {
+    // lane l folds partials l, l+32, ... (independent loads), then a fixed shuffle tree: deterministic
     double acc = 0.0;
-    for (unsigned i = 0; i < gridDim.x; ++i) acc += p.partial[i];
-    p.info[0] = static_cast<float>(acc / static_cast<double>(p.B));
-    *p.ticket = 0u;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += 32) acc += __ldcg(p.partial + i);
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) {
+      p.info[0] = static_cast<float>(acc / static_cast<double>(p.B));
+      *p.ticket = 0u;
+    }
   }
 }
 
@@ -322,7 +350,8 @@ TRL_API int64_t trl_ppo_actor_scratch_doubles(int64_t B, int act_dim) {
 TRL_API int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_stride, const float* actions,
                                const float* old_logp, const float* advs, const float* adv_stats,
                                const int* adv_stats_pos, int64_t B,
-                               int act_dim, int tanh_action, float clip_para, float entropy_coeff, float* g_mean,
+                               int act_dim, int tanh_action, float clip_para, float entropy_coeff, float ls_min,
+                               float ls_max, float* g_mean,
                                float* g_log_std, float* logp_out, float* info16, double* scratch, unsigned* ticket,
                                void* stream) {
   using namespace trl;
@@ -332,7 +361,7 @@ TRL_API int trl_ppo_actor_loss(const float* mean, const float* log_std, int ls_s
   TRL_REQUIRE(mean && log_std && actions && advs && g_mean && g_log_std && info16 && scratch && ticket,
               "trl_ppo_actor_loss: null pointer");
   ActorParams p{mean, log_std, actions, old_logp, advs, adv_stats, adv_stats_pos, g_mean, g_log_std, logp_out, info16, scratch,
-                ticket, B, act_dim, ls_stride, tanh_action, clip_para, entropy_coeff};
+                ticket, B, act_dim, ls_stride, tanh_action, clip_para, entropy_coeff, ls_min, ls_max};
   ppo_actor_loss_kernel<<<static_cast<unsigned>(ceil_div<long long>(B, kLossThreads)), kLossThreads, 0,
                           static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("ppo_actor_loss_kernel");

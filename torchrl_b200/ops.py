@@ -225,9 +225,11 @@ class LossScratch:
 
 
 def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para, entropy_coeff, tanh_action,
-                   scratch, g_mean=None, g_log_std=None, info=None, logp_out=None, stats_pos=None):
+                   scratch, g_mean=None, g_log_std=None, info=None, logp_out=None, stats_pos=None, ls_clamp=None):
     """PPO clipped-surrogate loss value, dL/dmean, dL/dlog_std and logged stats in one launch
-    (/root/reference/torchrl/algo/on_policy/ppo.py:41-91)."""
+    (/root/reference/torchrl/algo/on_policy/ppo.py:41-91).  ls_clamp=(lo, hi): `log_std` is the raw parameter, the
+    policy's torch.clamp is applied inside the kernel and g_log_std is the gradient of the raw parameter."""
+    ls_lo, ls_hi = (1.0, -1.0) if ls_clamp is None else (float(ls_clamp[0]), float(ls_clamp[1]))
     B, a = mean.shape
     assert scratch.B >= B and scratch.a == a
     ls_stride = 0 if log_std.dim() == 1 else a
@@ -241,7 +243,7 @@ def ppo_actor_loss(mean, log_std, actions, old_logp, advs, adv_stats, clip_para,
               _chk(actions, F32, "actions"), _opt(old_logp, F32, "old_logp"), _chk(advs, F32, "advs"),
               _opt(adv_stats, F32, "adv_stats"), _opt(stats_pos, I32, "stats_pos"), B, a, int(bool(tanh_action)),
               float(clip_para),
-              float(entropy_coeff), _chk(g_mean, F32, "g_mean"), _chk(g_log_std, F32, "g_log_std"),
+              float(entropy_coeff), ls_lo, ls_hi, _chk(g_mean, F32, "g_mean"), _chk(g_log_std, F32, "g_log_std"),
               _opt(logp_out, F32, "logp_out"), _chk(info, F32, "info"), _chk(scratch.actor, F64, "scratch"),
               scratch.tickets[0:1].data_ptr(), _stream())
     return g_mean, g_log_std, info
