@@ -108,6 +108,10 @@ int trl_row_gather(int nkeys, const void* const* src, void* const* dst, const in
                    const int64_t* idx, const int* pos_ptr, int rows, void* stream);
 int trl_ring_write(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
                    const int* row_ptr, void* stream);
+/* trl_ring_write + trl_step_advance(row_ptr, T, size_ptr) in one launch (the last CTA to finish advances the index);
+ * ticket: one unsigned, zero-initialised once by the caller. */
+int trl_ring_write_advance(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                           int* row_ptr, int T, int* size_ptr, unsigned* ticket, void* stream);
 /* mean, unbiased std, max, min of a vector (algo/on_policy/ppo.py:141-147). */
 int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream);
 /* K12: the same statistics over the union of all ranks' minibatches: local raw moments [sum, sumsq, max, -min]

@@ -51,9 +51,9 @@ def _batches(n, B, seed, lead=None):
 
 
 def _reference_agent(kind, tmp_path, **algo_kw):
-    import gym
     import torch
-    reference_loader.load()
+    reference_loader.load()                  # puts the gym / tensorboardX shims on sys.path
+    import gym
     import torchrl.networks as networks
     import torchrl.policies as policies
     from torchrl.algo import A2C, TRPO, VMPO

@@ -179,6 +179,29 @@ def test_flat_adam_matches_torch_adam_with_clipping():
 
 
 @pytest.mark.gpu
+def test_ring_write_advance_is_write_then_advance():
+    import torch
+    from torchrl_b200 import ops
+    dev = "cuda"
+    T = 5
+    src_a = torch.zeros(1, 40000, device=dev)
+    src_b = torch.zeros(1, 7, dtype=torch.float64, device=dev)
+    ring_a = torch.zeros(T, 40000, device=dev)
+    ring_b = torch.zeros(T, 7, dtype=torch.float64, device=dev)
+    plan = ops.RowCopyPlan([src_a, src_b], [ring_a, ring_b], [40000 * 4, 7 * 8])
+    pos = torch.zeros(1, dtype=torch.int32, device=dev)
+    size = torch.zeros(1, dtype=torch.int32, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    for i in range(7):
+        src_a.fill_(i + 1.0)
+        src_b.fill_(-(i + 1.0))
+        ops.ring_write_advance(plan, pos, T, ticket, size_ptr=size)
+        assert int(pos) == (i + 1) % T and int(size) == min(i + 1, T) and int(ticket) == 0
+        assert float(ring_a[i % T].min()) == float(ring_a[i % T].max()) == i + 1.0
+        assert float(ring_b[i % T].max()) == -(i + 1.0)
+
+
+@pytest.mark.gpu
 def test_polyak_update_matches_formula():
     import torch
     from torchrl_b200 import ops

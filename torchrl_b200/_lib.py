@@ -44,6 +44,7 @@ SIGNATURES = {
     "trl_step_advance": [vp, i32, vp, vp, vp],
     "trl_row_gather": [i32, vp, vp, vp, vp, vp, i32, vp],
     "trl_ring_write": [i32, vp, vp, vp, vp, vp],
+    "trl_ring_write_advance": [i32, vp, vp, vp, vp, i32, vp, vp, vp],
     "trl_vec_stats": [vp, i64, vp, vp],
     "trl_vec_moments": [vp, i64, vp, vp],
     "trl_vec_stats_from_moments": [vp, i32, f64, vp, vp],

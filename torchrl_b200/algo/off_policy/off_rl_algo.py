@@ -48,6 +48,7 @@ class OffRLAlgo(RLAlgo):
             "idx": torch.zeros(U * b, dtype=torch.int64, device=dev),
             "idx_host": torch.zeros(U * b, dtype=torch.int64).pin_memory(),
             "upd": torch.zeros(1, dtype=torch.int32, device=dev),
+            "log_ticket": torch.zeros(1, dtype=torch.int32, device=dev),
             "info": torch.zeros(1, self.INFO_SLOTS, dtype=torch.float32, device=dev),
             "log32": torch.zeros(U, self.INFO_SLOTS, dtype=torch.float32, device=dev),
             "scratch": ops.OffPolicyScratch(b * N, dev),
@@ -61,8 +62,7 @@ class OffRLAlgo(RLAlgo):
 
     def _finish_update(self):
         ub = self._ub
-        ops.ring_write(ub["log_plan"], ub["upd"])
-        ops.counter_advance(None, ub["upd"], ub["U"])
+        ops.ring_write_advance(ub["log_plan"], ub["upd"], ub["U"], ub["log_ticket"])     # log row, then upd += 1
 
     def _variant(self):
         """Key of the update-graph variant for the current update (e.g. TD3's delayed actor step)."""

@@ -152,6 +152,7 @@ class A2C(OnRLAlgo):
             "perm_host": torch.zeros(passes * T, dtype=torch.int64).pin_memory(),
             "upd": torch.zeros(1, dtype=torch.int32, device=dev),
             "info": torch.zeros(1, 64, dtype=torch.float32, device=dev),
+            "log_ticket": torch.zeros(1, dtype=torch.int32, device=dev),
             "log32": torch.zeros(U, 64, dtype=torch.float32, device=dev),
             "log64": torch.zeros(U, self.opt.sumsq3.numel(), dtype=torch.float64, device=dev),
             "scratch": ops.LossScratch(b * N, a, dev),
@@ -190,8 +191,7 @@ class A2C(OnRLAlgo):
             if self.dist is not None:
                 scale, fused_norm = self.dist.reduce_grads(self.opt, self._step_mask())   # exchange + norms, one kernel
             self.opt.step(active_mask=self._step_mask(), grad_scale=scale, reduced=fused_norm)
-            ops.ring_write(st["log_plan"], st["upd"])
-            ops.counter_advance(None, st["upd"], st["U"])
+            ops.ring_write_advance(st["log_plan"], st["upd"], st["U"], st["log_ticket"])   # log row, then upd += 1
 
     def _run_minibatch(self):
         if not self.use_cuda_graph:

@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(kThreads) allreduce_grad_kernel(const GradPara
       if (p.step) {
         const int st = p.step[k] + 1;
         p.step[k] = st;
-        p.sumsq3[p.seg.nseg + 2 * k] = 1.0 - pow(p.beta1, static_cast<double>(st));
-        p.sumsq3[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow(p.beta2, static_cast<double>(st)));
+        p.sumsq3[p.seg.nseg + 2 * k] = 1.0 - pow_int(p.beta1, st);
+        p.sumsq3[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow_int(p.beta2, st));
       }
     }
   }

@@ -59,6 +59,19 @@ __device__ __forceinline__ float tanh_ex2(float x) {
   return fmaf(-2.f, r, 1.f);
 }
 
+// b^n for a small positive integer n by repeated squaring (<= 2*log2(n) fp64 multiplies, a few ulp of double):
+// Adam's bias corrections 1 - beta^t.  libdevice pow(double, double) is several hundred dependent fp64 instructions,
+// which on one thread is microseconds -- on the serial tail of every optimizer step.
+__device__ __forceinline__ double pow_int(double b, int n) {
+  double r = 1.0;
+  while (n > 0) {
+    if (n & 1) r *= b;
+    b *= b;
+    n >>= 1;
+  }
+  return r;
+}
+
 // ---- warp / block reductions -------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

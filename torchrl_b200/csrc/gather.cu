@@ -27,6 +27,11 @@ struct RowCopyParams {
   int rows;                        // number of rows moved
   int scatter;                     // 0: dst[k] = src[idx[k]] ; 1: dst[idx[k]] = src[k]
   long long src_rows;              // rows in the gather source (bounds check), 0 = unchecked
+  // ring write + advance in one launch: the last CTA to finish bumps the row index it has just been used with
+  int* adv_ptr;                    // nullptr: plain copy; else *adv_ptr = (*adv_ptr + 1) % adv_T after ALL copies
+  int adv_T;
+  int* adv_size;                   // optional ring fill count, saturating at adv_T
+  unsigned* ticket;                // zero between launches (with adv_ptr)
 };
 
 template <typename V>
@@ -52,13 +57,27 @@ __global__ void __launch_bounds__(256) row_copy_kernel(const RowCopyParams p) {
   long long per = ceil_div<long long>(rb, gridDim.x);
   per = (per + 15) & ~15LL;
   const long long lo = per * blockIdx.x;
-  if (lo >= rb) return;
-  const long long len = min(per, rb - lo);
-  s += lo; d += lo;
-  const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(len);
-  if ((al & 15) == 0) copy_units<uint4>(s, d, len, threadIdx.x, blockDim.x);
-  else if ((al & 3) == 0) copy_units<unsigned>(s, d, len, threadIdx.x, blockDim.x);
-  else copy_units<unsigned char>(s, d, len, threadIdx.x, blockDim.x);
+  if (lo < rb) {
+    const long long len = min(per, rb - lo);
+    s += lo; d += lo;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d) | static_cast<uintptr_t>(len);
+    if ((al & 15) == 0) copy_units<uint4>(s, d, len, threadIdx.x, blockDim.x);
+    else if ((al & 3) == 0) copy_units<unsigned>(s, d, len, threadIdx.x, blockDim.x);
+    else copy_units<unsigned char>(s, d, len, threadIdx.x, blockDim.x);
+  }
+  if (p.adv_ptr) {
+    // every CTA has read *row_ptr by now; the last one to arrive advances it (one launch instead of copy + advance)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+      if (atomicAdd(p.ticket, 1u) == total - 1) {
+        *p.adv_ptr = (*p.adv_ptr + 1) % p.adv_T;
+        if (p.adv_size && *p.adv_size < p.adv_T) *p.adv_size += 1;
+        *p.ticket = 0u;
+      }
+    }
+  }
 }
 
 // stats[0..3] = mean, unbiased std, max, min of x[0..n)   (one CTA; fp64 accumulation)
@@ -194,7 +213,8 @@ __global__ void group_stats_from_moments_kernel(const double* __restrict__ g, in
 
 static int launch_row_copy(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
                            const int64_t* idx, const int* pos_ptr, const int* row_ptr, int rows, int scatter,
-                           void* stream, const char* who) {
+                           void* stream, const char* who, int* adv_ptr = nullptr, int adv_T = 1, int* adv_size = nullptr,
+                           unsigned* ticket = nullptr) {
   using namespace trl;
   TRL_REQUIRE(nkeys >= 1 && nkeys <= kMaxKeys, "%s: nkeys %d not in 1..%d", who, nkeys, kMaxKeys);
   TRL_REQUIRE(rows >= 0, "%s: negative row count", who);
@@ -216,6 +236,7 @@ static int launch_row_copy(int nkeys, const void* const* src, void* const* dst, 
   p.rows = rows;
   p.scatter = scatter;
   p.src_rows = 0;
+  p.adv_ptr = adv_ptr; p.adv_T = adv_T; p.adv_size = adv_size; p.ticket = ticket;
   // ~16 KB per CTA, but never more CTAs than ~8 waves of the chip
   long long chunks = ceil_div<long long>(max_rb, 16384);
   const long long cap = ceil_div<long long>(8LL * kNumSM, static_cast<long long>(rows) * nkeys);
@@ -234,6 +255,16 @@ TRL_API int trl_ring_write(int nkeys, const void* const* src, void* const* dst, 
                            const int* row_ptr, void* stream) {
   TRL_REQUIRE(row_ptr, "trl_ring_write: null row pointer");
   return launch_row_copy(nkeys, src, dst, row_bytes, nullptr, nullptr, row_ptr, 1, 1, stream, "trl_ring_write");
+}
+
+// trl_ring_write followed by trl_step_advance(row_ptr, T, size_ptr) in ONE launch: every key's row is written at
+// *row_ptr, then (after all copies) *row_ptr = (*row_ptr + 1) % T and, if given, *size_ptr = min(*size_ptr + 1, T).
+// ticket: one unsigned, zero-initialised once by the caller.
+TRL_API int trl_ring_write_advance(int nkeys, const void* const* src, void* const* dst, const int64_t* row_bytes,
+                                   int* row_ptr, int T, int* size_ptr, unsigned* ticket, void* stream) {
+  TRL_REQUIRE(row_ptr && ticket && T >= 1, "trl_ring_write_advance: null pointer or T < 1");
+  return launch_row_copy(nkeys, src, dst, row_bytes, nullptr, nullptr, row_ptr, 1, 1, stream, "trl_ring_write_advance",
+                         row_ptr, T, size_ptr, ticket);
 }
 
 TRL_API int trl_vec_stats(const float* x, int64_t n, float* stats4, void* stream) {

@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(kOffThreads) sac_alpha_step_kernel(const Alpha
     const float step = p.state[2] + 1.f;
     const float m = p.beta1 * p.state[0] + (1.f - p.beta1) * g;
     const float vv = p.beta2 * p.state[1] + (1.f - p.beta2) * g * g;
-    const double bc1 = 1.0 - pow(static_cast<double>(p.beta1), static_cast<double>(step));
-    const double bc2 = 1.0 - pow(static_cast<double>(p.beta2), static_cast<double>(step));
+    const double bc1 = 1.0 - pow_int(static_cast<double>(p.beta1), step);
+    const double bc2 = 1.0 - pow_int(static_cast<double>(p.beta2), step);
     const float denom = sqrtf(vv) / static_cast<float>(sqrt(bc2)) + p.eps;
     const float la_new = la - (p.lr / static_cast<float>(bc1)) * (m / denom);
     p.state[0] = m; p.state[1] = vv; p.state[2] = step;

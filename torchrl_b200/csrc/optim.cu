@@ -86,8 +86,8 @@ __global__ void __launch_bounds__(kOptThreads) grad_sumsq_kernel(const SumsqPara
         const int st = p.step[k] + 1;
         p.step[k] = st;
         // bias corrections in fp64 once per segment (torch computes them in Python floats)
-        p.out[p.seg.nseg + 2 * k] = 1.0 - pow(p.beta1, static_cast<double>(st));
-        p.out[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow(p.beta2, static_cast<double>(st)));
+        p.out[p.seg.nseg + 2 * k] = 1.0 - pow_int(p.beta1, st);
+        p.out[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow_int(p.beta2, st));
       }
     }
   }
@@ -120,6 +120,26 @@ __device__ __forceinline__ void split_tf32_store(float w, float* __restrict__ hi
   lo[i] = w - h;
 }
 
+__device__ __forceinline__ void adam_element(const AdamParams& p, long long i, int s, float norm_s, float bc1,
+                                             float bc2_sqrt) {
+  float g = p.g[i] * p.grad_scale;
+  if (p.max_norm[s] > 0.f) {
+    // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), applied only when < 1
+    const float total_norm = norm_s * fabsf(p.grad_scale);
+    const float coef = p.max_norm[s] / (total_norm + 1e-6f);
+    if (coef < 1.0f) g *= coef;
+  }
+  const float m = p.beta1 * p.m[i] + (1.0f - p.beta1) * g;
+  const float v = p.beta2 * p.v[i] + (1.0f - p.beta2) * g * g;
+  p.m[i] = m;
+  p.v[i] = v;
+  const float denom = sqrtf(v) / bc2_sqrt + p.eps[s];
+  const float w = p.w[i] - (p.lr[s] / bc1) * (m / denom);
+  p.w[i] = w;
+  if (p.w_hi) split_tf32_store(w, p.w_hi, p.w_lo, i);
+  if (p.zero_grad) p.g[i] = 0.f;
+}
+
 __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(const AdamParams p) {
   const long long total = p.seg.begin[p.seg.nseg];
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -128,24 +148,8 @@ __global__ void __launch_bounds__(kOptThreads) adam_step_kernel(const AdamParams
 #pragma unroll
     for (int k = 1; k < kMaxSeg; ++k) s += (k < p.seg.nseg && i >= p.seg.begin[k]) ? 1 : 0;
     if (!((p.active_mask >> s) & 1u)) continue;
-    float g = p.g[i] * p.grad_scale;
-    if (p.max_norm[s] > 0.f) {
-      // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), applied only when < 1
-      const float total_norm = static_cast<float>(sqrt(p.sumsq[s])) * fabsf(p.grad_scale);
-      const float coef = p.max_norm[s] / (total_norm + 1e-6f);
-      if (coef < 1.0f) g *= coef;
-    }
-    const float bc1 = static_cast<float>(p.sumsq[p.seg.nseg + 2 * s]);
-    const float bc2_sqrt = static_cast<float>(p.sumsq[p.seg.nseg + 2 * s + 1]);
-    const float m = p.beta1 * p.m[i] + (1.0f - p.beta1) * g;
-    const float v = p.beta2 * p.v[i] + (1.0f - p.beta2) * g * g;
-    p.m[i] = m;
-    p.v[i] = v;
-    const float denom = sqrtf(v) / bc2_sqrt + p.eps[s];
-    const float w = p.w[i] - (p.lr[s] / bc1) * (m / denom);
-    p.w[i] = w;
-    if (p.w_hi) split_tf32_store(w, p.w_hi, p.w_lo, i);
-    if (p.zero_grad) p.g[i] = 0.f;
+    adam_element(p, i, s, static_cast<float>(sqrt(p.sumsq[s])), static_cast<float>(p.sumsq[p.seg.nseg + 2 * s]),
+                 static_cast<float>(p.sumsq[p.seg.nseg + 2 * s + 1]));
   }
 }
 

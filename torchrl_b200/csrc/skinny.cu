@@ -253,17 +253,21 @@ __global__ void __launch_bounds__(256, 2) skinny_tn_kernel(const float* __restri
   }
 }
 
-// second stage: e indexes the k-major partial ([K][H] then K column sums).  CTA = 32 elements x 32 groups (1024
-// threads): group g sums partials g, g+32, ... with every load independent (a few hundred slabs => one or two rounds
-// of L2 latency instead of a 40-deep dependent chain), then warp 0 adds the 32 group sums in order.
+// second stage: e indexes the k-major partial ([K][H] then K column sums).  CTA = 8 elements x 32 groups (256 threads;
+// 8 consecutive floats = one 32-byte sector per slab): group g sums partials g, g+32, ... with every load independent
+// (a few hundred slabs => one or two rounds of L2 latency instead of a 40-deep dependent chain), then the first 8
+// threads add the 32 group sums in order.  Small CTAs on purpose: inside the minibatch graph this kernel starts while
+// the other network's kernels still hold most of every SM.
 constexpr int kRedGroups = 32;
-__global__ void __launch_bounds__(32 * kRedGroups) skinny_tn_reduce_kernel(const float* __restrict__ partial,
-                                                                          float* __restrict__ Out,
-                                                                          float* __restrict__ colsum, int n_cs, int nslab,
-                                                                          int H, int K, int out_transposed) {
-  __shared__ float red[kRedGroups][33];
-  const int el = threadIdx.x & 31, g = threadIdx.x >> 5;
-  const int e = blockIdx.x * 32 + el;
+constexpr int kRedElems = 8;
+__global__ void __launch_bounds__(kRedElems * kRedGroups) skinny_tn_reduce_kernel(const float* __restrict__ partial,
+                                                                                 float* __restrict__ Out,
+                                                                                 float* __restrict__ colsum, int n_cs,
+                                                                                 int nslab, int H, int K,
+                                                                                 int out_transposed) {
+  __shared__ float red[kRedGroups][kRedElems + 1];
+  const int el = threadIdx.x & (kRedElems - 1), g = threadIdx.x / kRedElems;
+  const int e = blockIdx.x * kRedElems + el;
   const int n_main = K * H;
   const int n_all = n_main + n_cs;                       // n_cs trailing entries of row K go to colsum[]
   const long long stride = static_cast<long long>(K + 1) * H;
@@ -519,7 +523,7 @@ static int launch_skinny_tn(const float* A, const float* Yact, const float* B, f
   if (rc != TRL_OK) return rc;
   const int n_cs = colsum ? (fused_act ? H : K) : 0;
   const int n_all = K * H + n_cs;
-  skinny_tn_reduce_kernel<<<ceil_div(n_all, 32), 32 * kRedGroups, 0, st>>>(scratch, Out, colsum, n_cs, nslab, H, K, out_transposed);
+  skinny_tn_reduce_kernel<<<ceil_div(n_all, kRedElems), kRedElems * kRedGroups, 0, st>>>(scratch, Out, colsum, n_cs, nslab, H, K, out_transposed);
   return check_launch("skinny_tn_reduce_kernel");
 }
 
@@ -599,6 +603,6 @@ TRL_API int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* 
   int rc = check_launch("skinny_n_dgrad_kernel");
   if (rc != TRL_OK) return rc;
   // column sums: partial [nslab][H] viewed as a K = 0 "tn" partial (stride H, all H entries are colsum entries)
-  skinny_tn_reduce_kernel<<<ceil_div(H, 32), 32 * kRedGroups, 0, st>>>(scratch, db, db, H, nslab, H, 0, 0);
+  skinny_tn_reduce_kernel<<<ceil_div(H, kRedElems), kRedElems * kRedGroups, 0, st>>>(scratch, db, db, H, nslab, H, 0, 0);
   return check_launch("skinny_tn_reduce_kernel");
 }

@@ -137,7 +137,9 @@ class FlatAdam(FlatParams):
     def step(self, active_mask=None, grad_scale=1.0, zero_grad=True, reduced=False):
         """clip (per segment, global norm) + Adam + zero the gradient: two launches.  reduced=True: the gradient
         exchange kernel (distributed.reduce_grads) has already left the summed gradient in `self.reduced` together
-        with its norms / step counts and zeroed `self.grad`: only the Adam launch remains."""
+        with its norms / step counts and zeroed `self.grad`: only the Adam launch remains.
+        (A one-launch variant with a grid barrier between the norm and the update was measured at 9.3 us against 7.5 us
+        for these two launches on the PPO agent's 141 k parameters, and dropped.)"""
         mask = self.all_mask if active_mask is None else int(active_mask)
         st = ops._stream()
         src = self.grad

@@ -204,6 +204,13 @@ def ring_write(plan, row_ptr):
     _lib.call("trl_ring_write", plan.n, plan.src, plan.dst, plan.rb, _chk(row_ptr, I32, "row_ptr"), _stream())
 
 
+def ring_write_advance(plan, row_ptr, T, ticket, size_ptr=None):
+    """ring_write(plan, row_ptr) then row_ptr = (row_ptr + 1) % T [, size = min(size + 1, T)] in one launch.
+    ticket: a zero-initialised int32[1] owned by the caller."""
+    _lib.call("trl_ring_write_advance", plan.n, plan.src, plan.dst, plan.rb, _chk(row_ptr, I32, "row_ptr"), int(T),
+              _opt(size_ptr, I32, "size_ptr"), _chk(ticket, I32, "ticket"), _stream())
+
+
 def vec_stats(x, out=None):
     """[mean, unbiased std, max, min] of a float vector, on the device."""
     if out is None:
