@@ -191,7 +191,7 @@ struct Params {
 template <bool AMN, bool BMN, bool BSPLIT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                  const __grid_constant__ CUtensorMap map_b2, const Params p) {
+                  const __grid_constant__ CUtensorMap map_b2, const __grid_constant__ CUtensorMap map_c, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   auto a_hi = [&](int s) { return smem + s * kStageBytes; };
@@ -220,6 +220,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b)) : "memory");
     if (BSPLIT) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_b2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -346,30 +347,32 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       if (ct == 0) TRL_TRACE(40 + kb);
     }
     // epilogue: TMEM lane quadrant of this warp = warp % 4.  The operand stages are free now (tmem_full fires after
-    // the last MMA of the pair has read them): this warp's 32 rows are parked there with a pitch of 260 floats.
+    // the last MMA of the pair has read them): the epilogue's output boxes are staged there.
     asm volatile("bar.sync 1, %0;" ::"n"(kWorkThreads) : "memory");   // the epilogue warps: bias_s is complete
     mbar_wait(tmem_full, 0);
     if (ct == 0) TRL_TRACE(2);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // Streaming epilogue, 32 columns at a time: TMEM -> registers (this thread = one accumulator row) -> bias /
-    // activation -> a warp-private (32 x 36) transposition buffer in the free operand stages -> global memory as
-    // 128-byte row segments (one 16-byte piece per lane, 4 rows per store instruction: every 32-byte sector written
-    // whole).  Stores of chunk c overlap the TMEM load and the MUFU work of chunk c + 1.
+    // activation -> a warp-private (32 rows x 128 bytes) box in the free operand stages, written in the 128-byte
+    // swizzle (16-byte piece j of row r at piece j ^ (r & 7): conflict-free STS.128) -> ONE TMA store per box
+    // (cp.async.bulk.tensor, full 128-byte lines, rows beyond M clipped by the tensor map).  No shared-memory read-back
+    // and no per-thread global stores: the copy engine drains box c while the warp loads and transforms box c + 1.
     // 4 warps per TMEM lane quadrant (a warp may only touch lanes 32 (warp % 4) ..): each takes 2 of the 8 chunks, so
     // that every SM sub-partition has 4 warps to hide the TMEM-load / MUFU / shared-memory latencies behind
     const int quad = warp & 3, sub = (warp - 2) >> 2;
     constexpr int kChunksPerWarp = (kBN / 32) / (kWorkWarps / 4);
-    constexpr int kTP = 36;                                // floats: conflict-free for the row-wise STS.128 AND LDS.128
-    const uint32_t tbuf = smem_u32(smem) + static_cast<uint32_t>((warp - 2) * 32 * kTP * 4);
-    const uint32_t my_row = tbuf + static_cast<uint32_t>(lane * kTP * 4);
-    const uint32_t rd = tbuf + static_cast<uint32_t>(((lane >> 3) * kTP + (lane & 7) * 4) * 4);
+    constexpr uint32_t kBoxBytes = 32 * 128;
+    static_assert(kWorkWarps * kChunksPerWarp * kBoxBytes <= static_cast<uint32_t>(kStages) * kStageBytes, "boxes fit in the stages");
+    const uint32_t boxes = smem_u32(smem) + static_cast<uint32_t>(warp - 2) * (kChunksPerWarp * kBoxBytes);
+    const uint32_t my_row = boxes + static_cast<uint32_t>(lane) * 128u;
+    const uint32_t swz = static_cast<uint32_t>(lane & 7) << 4;
     const uint32_t bias_addr = smem_u32(bias_s);
     const bool has_bias = p.bias != nullptr;
     const int act = p.act;
     const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const long long row0 = static_cast<long long>(m_blk) * kBM + quad * 32;
-    float* cbase = p.C + (static_cast<long long>(split) * p.M + row0 + (lane >> 3)) * kBN + (lane & 7) * 4;
-    const int nrows = (row0 + 32 <= p.M) ? 32 : static_cast<int>(p.M > row0 ? p.M - row0 : 0);
+    const int crow = static_cast<int>(static_cast<long long>(split) * p.M + row0);   // row coordinate in map_c
+    const bool any_rows = row0 < p.M;
 #define TRL_TMEM_LD32(R, ADDR)                                                                                        \
     asm volatile(                                                                                                     \
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                     \
@@ -390,7 +393,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       uint32_t (&cur)[32] = (cc & 1) ? rb : ra;
       uint32_t (&nxt)[32] = (cc & 1) ? ra : rb;
       if (cc + 1 < kChunksPerWarp) TRL_TMEM_LD32(nxt, taddr0 + static_cast<uint32_t>((c + 1) * 32));
-      __syncwarp();                                        // the previous chunk has been read out of the buffer
+      const uint32_t row_box = my_row + static_cast<uint32_t>(cc) * kBoxBytes;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 v = make_float4(__uint_as_float(cur[4 * j]), __uint_as_float(cur[4 * j + 1]), __uint_as_float(cur[4 * j + 2]),
@@ -404,18 +407,20 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
           }
         }
-        sts128(my_row + static_cast<uint32_t>(j * 16), v);
+        sts128(row_box + ((static_cast<uint32_t>(j) << 4) ^ swz), v);
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the copy engine
       __syncwarp();
-      float4 q[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = lds128(rd + static_cast<uint32_t>(i * 4 * kTP * 4));   // rows 4 i + lane / 8
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        if (4 * i + (lane >> 3) < nrows)
-          *reinterpret_cast<float4*>(cbase + static_cast<long long>(4 * i) * kBN + c * 32) = q[i];
+      if (lane == 0 && any_rows) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                     ::"l"(reinterpret_cast<uint64_t>(&map_c)), "r"(boxes + static_cast<uint32_t>(cc) * kBoxBytes),
+                       "r"(c * 32), "r"(crow)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
       if ((ct & 127) == 0 && lane == 0) TRL_TRACE(120 + c);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // boxes read before smem goes away
 #undef TRL_TMEM_LD32
     if (ct == 0) TRL_TRACE(3);
     if (ct == 0) TRL_TRACE(4);
@@ -493,6 +498,18 @@ static bool make_map(CUtensorMap* map, const float* base, uint64_t rows, uint64_
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the output (rows x 256) fp32 row-major: 32-column x 32-row boxes in the 128-byte swizzle, for the epilogue's TMA stores
+static bool make_map_c(CUtensorMap* map, float* base, uint64_t rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(kBN), rows};
+  const cuuint64_t gstride[1] = {kBN * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 #ifdef TRL_PAIR_TRACE
 static long long* g_trace = nullptr;
 static unsigned g_trace_cta = 0;
@@ -501,6 +518,11 @@ static unsigned g_trace_cta = 0;
 template <bool AMN, bool BMN, bool BSPLIT>
 static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mb2, const Params& p, unsigned ctas_m,
                   unsigned splits, cudaStream_t st, const char* what) {
+  CUtensorMap mc;
+  if (!make_map_c(&mc, p.C, static_cast<uint64_t>(splits) * static_cast<uint64_t>(p.M))) {
+    set_error("%s: cuTensorMapEncodeTiled failed for the output", what);
+    return TRL_EUNSUPPORTED;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm3_pair_kernel<AMN, BMN, BSPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -512,9 +534,9 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMa
   Params q = p;
   q.trace = g_trace;
   q.trace_cta = g_trace_cta;
-  gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, q);
+  gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, mc, q);
 #else
-  gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, p);
+  gemm3_pair_kernel<AMN, BMN, BSPLIT><<<dim3(ctas_m, splits), kThreads, kSmemBytes, st>>>(ma, mb, mb2, mc, p);
 #endif
   return check_launch(what);
 }
