@@ -245,6 +245,13 @@ int trl_allreduce_grad(const void* const* peer_data, void* const* peer_flags, in
  * gather == 0: out (n) = sum over ranks; gather != 0: out (world, n) = every rank's vector in rank order. */
 int trl_allreduce_f64(const void* const* peer_data, void* const* peer_flags, int rank, int world, double* out, int n,
                       int gather, unsigned* seq, void* stream);
+/* The same exchange for small vectors (n <= nmax) as ONE NVLink traversal: every rank pushes 16-byte packets
+ * {lo32, seq, hi32, seq} into slot [seq & 1][rank] of each peer's receive area and polls its own (NCCL's "LL" scheme; no
+ * barrier phases, no fences).  peer_recv: `world` device pointers to receive areas of trl_comm_ll_recv_bytes(world, nmax)
+ * zero-initialised bytes; ll_seq: device uint32 of the communicator counting LL exchanges. */
+int64_t trl_comm_ll_recv_bytes(int world, int nmax);
+int trl_allreduce_f64_ll(const double* local, void* const* peer_recv, int rank, int world, double* out, int n, int nmax,
+                         int gather, unsigned* ll_seq, void* stream);
 
 /* ---- fp32-faithful tensor-core GEMM for the 256-wide MLP layers (tcgen05.mma kind::tf32, 3xTF32 split in
  * shared memory, TMA operand loads, TMEM accumulator): C (M x 256) = A (M x K) . B (256 x K)^T, A/B row-major.

@@ -17,6 +17,8 @@ from torchrl_b200.distributed import DataParallelContext  # noqa: E402
 from torchrl_b200.networks import fused  # noqa: E402
 
 ctx = DataParallelContext()
+if ctx.rank != 0:
+    sys.stdout = open(os.devnull, "w")
 
 
 class A:

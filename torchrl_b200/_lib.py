@@ -81,6 +81,8 @@ SIGNATURES = {
     "trl_comm_scratch_doubles": [i32],
     "trl_allreduce_grad": [vp, vp, i32, i32, vp, i64, vp, i32, u32, vp, vp, f64, f64, vp, vp, vp, i32, vp],
     "trl_allreduce_f64": [vp, vp, i32, i32, vp, i32, i32, vp, vp],
+    "trl_comm_ll_recv_bytes": [i32, i32],
+    "trl_allreduce_f64_ll": [vp, vp, i32, i32, vp, i32, i32, i32, vp, vp],
     "trl_gemm3_pair": [vp, vp, vp, vp, i64, i64, i32, vp, i32, vp],
     "trl_gemm3_pair_tn": [vp, vp, vp, i64, i64, i32, vp, vp],
     "trl_skinny_k_fwd": [vp, vp, vp, vp, i64, i32, i32, i32, vp],
@@ -105,10 +107,10 @@ SIGNATURES = {
 _RESTYPES = {"trl_last_error": ctypes.c_char_p, "trl_ppo_actor_scratch_doubles": ctypes.c_int64,
              "trl_offpolicy_scratch_doubles": ctypes.c_int64, "trl_bias_act_bwd_scratch_floats": ctypes.c_int64,
              "trl_skinny_tn_scratch_floats": ctypes.c_int64,
-             "trl_skinny_dgrad_act_scratch_floats": ctypes.c_int64}
+             "trl_skinny_dgrad_act_scratch_floats": ctypes.c_int64, "trl_comm_ll_recv_bytes": ctypes.c_int64}
 # entry points that return a value rather than an error code
 _VALUE_FUNCS = ("trl_abi_version", "trl_synth_env_smem_bytes", "trl_synth_env_num_ctas", "trl_comm_flag_bytes",
-                "trl_comm_ipc_handle_bytes", "trl_comm_scratch_doubles",
+                "trl_comm_ipc_handle_bytes", "trl_comm_scratch_doubles", "trl_comm_ll_recv_bytes",
                 "trl_ppo_actor_scratch_doubles", "trl_grad_sumsq_blocks")
 
 _lib = None

@@ -17,15 +17,20 @@
 //   * block b raises flag[done][b][rank] everywhere and waits: "everybody has finished reading my operand", then
 //     zeroes its slice of the local operand (the gradient buffer is accumulated into by the next backward).
 // Flags carry a sequence number that only grows (kept in device memory, bumped by the last block), so nothing is
-// ever reset.  grid <= 64 blocks: all co-resident, the peer waits cannot deadlock on scheduling.
+// ever reset.  grid <= 148 blocks (one per SM): all co-resident, the peer waits cannot deadlock on scheduling.
 // Evidence in SASS: LDG / STG with .SYS scope on peer (IPC-mapped) addresses in the same kernel as the reduction.
+// Measured alone (scripts/comm_probe.py, 141 k floats, launch included): 14 us at W = 2, 20 us at W = 8 (NCCL all-reduce
+// of the same buffer, without the norms: 19 / 36 us).  Two variants were built and dropped: a reduce-scatter + all-gather
+// in two PUSH rounds of flag-carrying 16-byte packets (22 us at W = 2: NVLink sees 70 k small volatile stores per round),
+// and a deferred second phase on a side stream beside the Adam launch (no measurable gain).  The flag-in-payload push IS
+// the better scheme for the few-hundred-byte fp64 vectors (allreduce_f64_ll_kernel below: 3.5 us against 5.7 us).
 #include "common.cuh"
 
 namespace trl {
 namespace comm {
 
 constexpr int kMaxWorld = 8;
-constexpr int kMaxBlocks = 64;
+constexpr int kMaxBlocks = 148;                          // one block per SM at most: co-resident
 constexpr int kThreads = 256;
 constexpr int kMaxSeg = 8;
 constexpr int kFlagWords = 2 * kMaxBlocks * kMaxWorld;    // [phase][block][source rank] uint32
@@ -109,11 +114,16 @@ __global__ void __launch_bounds__(kThreads) allreduce_grad_kernel(const GradPara
 #pragma unroll
   for (int s = 0; s < kMaxSeg; ++s) acc[s] = 0.0;
   for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
-    float4 v = ld_peer_f4(static_cast<const float*>(p.pe.data[0]) + 4 * i);
-    for (int r = 1; r < p.world; ++r) {
-      const float4 w = ld_peer_f4(static_cast<const float*>(p.pe.data[r]) + 4 * i);
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-    }
+    // all W peer loads are issued before the first add (a load-add-load chain costs W NVLink round trips of ~2 us
+    // each: measured 39 us per minibatch at W = 8), then summed in rank order
+    float4 w[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) w[r] = ld_peer_f4(static_cast<const float*>(p.pe.data[r]) + 4 * i);
+    float4 v = w[0];
+#pragma unroll
+    for (int r = 1; r < kMaxWorld; ++r)
+      if (r < p.world) { v.x += w[r].x; v.y += w[r].y; v.z += w[r].z; v.w += w[r].w; }
     *reinterpret_cast<float4*>(p.out + 4 * i) = v;
     // segments start on 16-byte boundaries (flat.py), so a float4 never straddles two of them
     int s = 0;
@@ -136,37 +146,44 @@ __global__ void __launch_bounds__(kThreads) allreduce_grad_kernel(const GradPara
     for (int w = 0; w < kThreads / 32; ++w) t += sh[w][threadIdx.x];
     p.partial[blockIdx.x * p.seg.nseg + threadIdx.x] = t;
   }
+  // ---- last block to get here: per-segment totals, Adam step counts, bias corrections, sequence number.  Done BEFORE
+  // the second cross-rank phase so that this serial tail runs in the shadow of that phase's NVLink round trip.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (threadIdx.x < p.seg.nseg) {
+      const int k = threadIdx.x;
+      if ((p.active_mask >> k) & 1u) {
+        double t = 0.0;
+        for (unsigned b0 = 0; b0 < gridDim.x; b0 += 16) {    // 16 partials in flight, added in block order
+          double v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = (b0 + u < gridDim.x) ? __ldcg(p.partial + (b0 + u) * p.seg.nseg + k) : 0.0;
+#pragma unroll
+          for (int u = 0; u < 16; ++u) t += v[u];
+        }
+        p.sumsq3[k] = t;
+        if (p.step) {
+          const int st = p.step[k] + 1;
+          p.step[k] = st;
+          p.sumsq3[p.seg.nseg + 2 * k] = 1.0 - pow_int(p.beta1, st);
+          p.sumsq3[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow_int(p.beta2, st));
+        }
+      }
+    }
+    if (threadIdx.x == 0) {
+      *p.ticket = 0u;
+      *p.seq = seq;          // every block read the old value at its start (they all passed the ticket above)
+    }
+  }
   // ---- everybody has read my operand: it may be overwritten ------------------------------------------------------------
   cross_rank_barrier(p.pe, p.rank, p.world, 1, seq);
   if (p.zero_local)
     for (long long i = lo + threadIdx.x; i < hi; i += kThreads)
       *reinterpret_cast<float4*>(p.local + 4 * i) = make_float4(0.f, 0.f, 0.f, 0.f);
-  // ---- last block: per-segment totals, Adam step counts, bias corrections, sequence number --------------------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  if (threadIdx.x < p.seg.nseg) {
-    const int k = threadIdx.x;
-    if ((p.active_mask >> k) & 1u) {
-      double t = 0.0;
-      for (unsigned b = 0; b < gridDim.x; ++b) t += p.partial[b * p.seg.nseg + k];
-      p.sumsq3[k] = t;
-      if (p.step) {
-        const int st = p.step[k] + 1;
-        p.step[k] = st;
-        p.sumsq3[p.seg.nseg + 2 * k] = 1.0 - pow_int(p.beta1, st);
-        p.sumsq3[p.seg.nseg + 2 * k + 1] = sqrt(1.0 - pow_int(p.beta2, st));
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    *p.ticket = 0u;
-    *p.seq = seq;
-  }
 }
 
 struct VecParams {
@@ -183,16 +200,83 @@ __global__ void __launch_bounds__(kThreads) allreduce_f64_kernel(const VecParams
   const unsigned seq = *p.seq + 1u;
   cross_rank_barrier(p.pe, p.rank, p.world, 0, seq);
   for (int i = threadIdx.x; i < p.n; i += kThreads) {
+    double w[kMaxWorld];                                 // every peer's value requested before the first use
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) w[r] = ld_peer_f64(static_cast<const double*>(p.pe.data[r]) + i);
     if (p.gather) {
-      for (int r = 0; r < p.world; ++r) p.out[r * p.n + i] = ld_peer_f64(static_cast<const double*>(p.pe.data[r]) + i);
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < p.world) p.out[r * p.n + i] = w[r];
     } else {
       double v = 0.0;
-      for (int r = 0; r < p.world; ++r) v += ld_peer_f64(static_cast<const double*>(p.pe.data[r]) + i);
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < p.world) v += w[r];
       p.out[i] = v;
     }
   }
   cross_rank_barrier(p.pe, p.rank, p.world, 1, seq);
   if (threadIdx.x == 0) *p.seq = seq;
+}
+
+// ---- small vectors: PUSH with the flag inside the payload (the "LL" scheme NCCL uses for latency-bound sizes) ----------
+// Every double travels as one 16-byte store {lo32, seq, hi32, seq}: each 8-byte half carries its own flag, so a reader
+// that sees both flags equal to this exchange's sequence number holds valid data -- no fence between data and flag, no
+// separate barrier.  A rank WRITES its vector into slot [parity][rank] of every peer's receive area (remote stores are
+// fire-and-forget: one NVLink traversal) and then polls its OWN receive area (local memory) for the W contributions.
+// Two parities: a rank starts exchange k+2 only after it has finished k+1, which needed every peer's k+1 data, which a
+// peer sends only after it has finished reading exchange k (stream order on that peer) -- so slot k%2 is free again.
+struct LLParams {
+  void* recv[kMaxWorld];           // receive area of every rank: [2][world][nmax] x 16 bytes
+  const double* __restrict__ local;
+  double* __restrict__ out;        // gather == 0: (n) sum in rank order; gather != 0: (world, n)
+  int n, nmax, rank, world, gather;
+  unsigned* __restrict__ ll_seq;   // device counter of LL exchanges of this communicator
+};
+
+constexpr int kLLThreads = 512;
+
+__global__ void __launch_bounds__(kLLThreads) allreduce_f64_ll_kernel(const LLParams p) {
+  const unsigned seq = *p.ll_seq + 1u;
+  const long long slot0 = static_cast<long long>(seq & 1u) * p.world;
+  for (int i = threadIdx.x; i < p.n; i += kLLThreads) {
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(p.local[i]));
+    const unsigned lo = static_cast<unsigned>(bits), hi = static_cast<unsigned>(bits >> 32);
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) {
+        char* dst = static_cast<char*>(p.recv[r]) + ((slot0 + p.rank) * p.nmax + i) * 16;
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(lo), "r"(seq), "r"(hi), "r"(seq) : "memory");
+      }
+  }
+  const char* mine = static_cast<const char*>(p.recv[p.rank]);
+  for (int i = threadIdx.x; i < p.n; i += kLLThreads) {
+    double w[kMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kMaxWorld; ++r)
+      if (r < p.world) {
+        const char* src = mine + ((slot0 + r) * p.nmax + i) * 16;
+        unsigned a, fa, b, fb;
+        do {
+          asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
+        } while (fa != seq || fb != seq);
+        w[r] = __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(b) << 32) | a));
+      }
+    if (p.gather) {
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < p.world) p.out[r * p.n + i] = w[r];
+    } else {
+      double v = 0.0;
+#pragma unroll
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (r < p.world) v += w[r];
+      p.out[i] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *p.ll_seq = seq;
 }
 
 static bool fill_peers(Peers& pe, const void* const* data, void* const* flags, int world) {
@@ -256,6 +340,13 @@ TRL_API int trl_comm_ipc_close(void* ptr) {
   return TRL_OK;
 }
 
+static unsigned grad_blocks(long long n) {
+  long long blocks = trl::ceil_div<long long>(n / 4, 1LL * trl::comm::kThreads);   // one float4 per thread while the SMs last
+  if (blocks > trl::comm::kMaxBlocks) blocks = trl::comm::kMaxBlocks;
+  if (blocks < 1) blocks = 1;
+  return static_cast<unsigned>(blocks);
+}
+
 TRL_API int trl_comm_scratch_doubles(int nseg) { return trl::comm::kMaxBlocks * (nseg > 0 ? nseg : 1); }
 
 // out (n floats) = sum over ranks of peer_data[r] (rank order), sumsq3 as trl_grad_sumsq computes it for `out`; this
@@ -281,10 +372,7 @@ TRL_API int trl_allreduce_grad(const void* const* peer_data, void* const* peer_f
   p.local = static_cast<float*>(const_cast<void*>(peer_data[rank]));
   p.out = out; p.n = n; p.active_mask = active_mask; p.partial = scratch; p.sumsq3 = sumsq3_out; p.step = step_counts;
   p.beta1 = beta1; p.beta2 = beta2; p.ticket = ticket; p.seq = seq; p.zero_local = zero_local;
-  long long blocks = ceil_div<long long>(n / 4, 2LL * kThreads);     // >= 2 float4 per thread
-  if (blocks > kMaxBlocks) blocks = kMaxBlocks;
-  if (blocks < 1) blocks = 1;
-  allreduce_grad_kernel<<<static_cast<unsigned>(blocks), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  allreduce_grad_kernel<<<grad_blocks(n), kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("allreduce_grad_kernel");
 }
 
@@ -299,4 +387,26 @@ TRL_API int trl_allreduce_f64(const void* const* peer_data, void* const* peer_fl
   p.rank = rank; p.world = world; p.out = out; p.n = n; p.gather = gather; p.seq = seq;
   allreduce_f64_kernel<<<1, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
   return check_launch("allreduce_f64_kernel");
+}
+
+// The same exchange for SMALL vectors (n <= nmax) with the flag carried inside every 16-byte packet: one NVLink traversal,
+// no barrier phases (see allreduce_f64_ll_kernel).  peer_recv: host array of `world` device pointers to the ranks' receive
+// areas of trl_comm_ll_recv_bytes(world, nmax) bytes each (zero-initialised); ll_seq: device uint32 of the communicator
+// (starts at 0, counts LL exchanges only).
+TRL_API int64_t trl_comm_ll_recv_bytes(int world, int nmax) { return 2LL * world * nmax * 16; }
+
+TRL_API int trl_allreduce_f64_ll(const double* local, void* const* peer_recv, int rank, int world, double* out, int n,
+                                 int nmax, int gather, unsigned* ll_seq, void* stream) {
+  using namespace trl;
+  using namespace trl::comm;
+  TRL_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, "trl_allreduce_f64_ll: bad rank / world");
+  TRL_REQUIRE(n >= 1 && n <= nmax && local && peer_recv && out && ll_seq, "trl_allreduce_f64_ll: bad arguments (n=%d nmax=%d)", n, nmax);
+  LLParams p;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    p.recv[r] = r < world ? peer_recv[r] : nullptr;
+    TRL_REQUIRE(r >= world || (p.recv[r] && aligned16(p.recv[r])), "trl_allreduce_f64_ll: receive areas must be 16-byte aligned");
+  }
+  p.local = local; p.out = out; p.n = n; p.nmax = nmax; p.rank = rank; p.world = world; p.gather = gather; p.ll_seq = ll_seq;
+  allreduce_f64_ll_kernel<<<1, kLLThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  return check_launch("allreduce_f64_ll_kernel");
 }

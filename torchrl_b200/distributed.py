@@ -69,6 +69,11 @@ class PeerComm:
         self.flag_ptrs = (ctypes.c_void_p * self.world)(*self.bases)
         self.seq = torch.zeros(1, dtype=torch.int32, device=dev)
         self.regions = {}
+        # receive area of the flag-in-payload exchange of small fp64 vectors (all_reduce_f64), zero from trl_comm_alloc
+        self._ll_recv = self.region("__ll_recv__", int(self.lib.trl_comm_ll_recv_bytes(self.world, self.LL_NMAX)),
+                                    torch.uint8)[1]
+        self._ll_seq = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
         dist.barrier()                      # every rank has mapped every block before anyone launches on them
 
     def region(self, name, nbytes, dtype):
@@ -85,10 +90,18 @@ class PeerComm:
         self.regions[name] = (local, ptrs)
         return self.regions[name]
 
+    LL_NMAX = 2048
+
     def all_reduce_f64(self, name, n, out, gather=False):
-        """out = sum over ranks (or the (W, n) stack when gather) of the first n doubles of region `name`."""
+        """out = sum over ranks (or the (W, n) stack when gather) of the first n doubles of region `name`.  Up to
+        LL_NMAX doubles travel as flag-carrying 16-byte packets pushed into the peers' receive areas (one NVLink
+        traversal, no barrier phases: trl_allreduce_f64_ll); longer vectors take the two-phase pull kernel."""
         from . import _lib, ops
-        _, ptrs = self.regions[name]
+        local, ptrs = self.regions[name]
+        if int(n) <= self.LL_NMAX:
+            _lib.call("trl_allreduce_f64_ll", local.data_ptr(), self._ll_recv, self.rank, self.world, out.data_ptr(),
+                      int(n), self.LL_NMAX, int(bool(gather)), self._ll_seq.data_ptr(), ops._stream())
+            return out
         _lib.call("trl_allreduce_f64", ptrs, self.flag_ptrs, self.rank, self.world, out.data_ptr(), int(n),
                   int(bool(gather)), self.seq.data_ptr(), ops._stream())
         return out
