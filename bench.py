@@ -591,6 +591,9 @@ def secondary_measurements(args, device):
     return out
 
 
+SETTLE_EPOCHS = 30        # untimed epochs between the W warm-up steps and the first timed leg (see run_ours)
+
+
 def run_ours(args):
     import torch
     from torchrl_b200 import _lib
@@ -627,40 +630,52 @@ def run_ours(args):
     sampler.start()
     for _ in range(max(args.warmup, 3)):
         epoch(True)
-    for _ in range(2):
-        epoch(False)
+    # settle: with several ranks the first ~2 s of the job are not steady (whichever leg ran first -- right behind 3
+    # warm-up epochs -- came out 10-80 % slow in 1 run of 3, per-step times flat inside the run; the second leg never
+    # did).  A fixed number of extra untimed epochs (the same on every rank: they contain collectives) covers it.
+    for _ in range(SETTLE_EPOCHS):
+        epoch(True)
     torch.cuda.synchronize(device)
-
-    # ---- value: device-timed, host out of the loop ------------------------------------------
-    launches0 = _lib.launch_count()
-    ctx.barrier()
-    torch.cuda.synchronize(device)
-    sampler.mark_begin()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        epoch(False)
-        if os.environ.get("BENCH_VALUE_SYNC", "1") == "1":
-            # bound the launch queue: wait (no data copied) until the epoch has drained before queueing
-            # the next ~450 graph launches; an unbounded queue measured ~15% slower on B200
-            torch.cuda.current_stream(device).synchronize()
-    ev1.record()
-    torch.cuda.synchronize(device)
-    sampler.mark_end()
-    ctx.barrier()
-    clocks = sampler.stop()
-    t_dev = ctx.max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
-    launches = _lib.launch_count() - launches0
 
     # ---- e2e: public API, wall clock, host copies inside ---------------------------------------
     ctx.barrier()
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for _ in range(args.steps):
+        t1 = time.perf_counter()
         epoch(True)
+        e2e_step_ms.append(round((time.perf_counter() - t1) * 1e3, 3))
     torch.cuda.synchronize(device)
     ctx.barrier()
     t_e2e = ctx.max_over_ranks(time.perf_counter() - t0)
+
+    # ---- value: device-timed, host out of the loop ------------------------------------------
+    # (second, after its own warm-up epochs: measured first, right behind the job's start-up, this leg was bistable
+    # with several ranks -- 1 run in 3 came out 20-50 % slower than the public-API leg that followed it)
+    for _ in range(max(args.warmup, 3)):
+        epoch(False)
+    torch.cuda.synchronize(device)
+    launches0 = _lib.launch_count()
+    ctx.barrier()
+    torch.cuda.synchronize(device)
+    sampler.mark_begin()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    marks[0].record()
+    for k in range(args.steps):
+        epoch(False)
+        marks[k + 1].record()
+        if os.environ.get("BENCH_VALUE_SYNC", "1") == "1":
+            # bound the launch queue: wait (no data copied) until the epoch has drained before queueing
+            # the next ~450 graph launches; an unbounded queue measured ~15% slower on B200
+            torch.cuda.current_stream(device).synchronize()
+    torch.cuda.synchronize(device)
+    sampler.mark_end()
+    ctx.barrier()
+    clocks = sampler.stop()
+    t_dev = ctx.max_over_ranks(marks[0].elapsed_time(marks[-1]) * 1e-3)
+    step_ms = [round(marks[k].elapsed_time(marks[k + 1]), 3) for k in range(args.steps)]    # this rank's steps
+    launches = _lib.launch_count() - launches0
 
     value = frames_per_step * args.steps / t_dev
     e2e_value = frames_per_step * args.steps / t_e2e
@@ -716,7 +731,10 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.envs_per_gpu, ctx.world_size),
                        "global_envs": args.envs_per_gpu * ctx.world_size,
-                       "parallelism": "dp%d (env sharding, NCCL all-reduce of the flat gradient)" % ctx.world_size,
+                       "untimed_epochs": "%d warm-up + %d settling epochs before the first timed leg (e2e), %d more before "
+                                         "the device-timed leg" % (max(args.warmup, 3), SETTLE_EPOCHS, max(args.warmup, 3)),
+                       "parallelism": "dp%d (env sharding; flat gradient summed by a one-shot all-reduce over NVLink peer memory fused "
+                                      "with the gradient norms, csrc/comm.cu)" % ctx.world_size,
                        "matmul": {"fp32": "fp32 cuBLAS SIMT (TF32 off)",
                                   "tf32x3": "3xTF32 error-compensated tensor-core GEMMs (fp32-faithful), cuBLAS",
                                   "tc3": "256-wide layers: hand-written tcgen05 3xTF32 GEMM on CTA pairs (fp32-faithful, "
@@ -726,6 +744,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": t_e2e / args.steps * 1e3},
             "gpu_launches": launches,
+            "step_ms": step_ms,
+            "e2e_step_ms": e2e_step_ms,
             "clocks": clocks,
         }
         if roofline is not None:
