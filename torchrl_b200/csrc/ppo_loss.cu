@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
     }
   }
   __syncthreads();
+  // the scalar outputs are independent of one another: a few threads compute them side by side (one thread doing all the
+  // fp64 divisions and square roots in sequence was ~2 us of this kernel's serial tail)
+  const double Bn = static_cast<double>(p.B);
+  const double* t = p.partial;
   if (threadIdx.x == 0) {
-    const double Bn = static_cast<double>(p.B);
-    const double* t = p.partial;
     // entropy of the Normal: sum_j (0.5 + 0.5 log 2pi + ls_j), averaged over the batch
     double ent_mean, ls_mean, ls_std, ls_max, ls_min;
     if (p.ls_stride) {
@@ -256,29 +258,30 @@ __global__ void __launch_bounds__(kLossThreads) ppo_actor_loss_kernel(const Acto
       ls_std = a > 1 ? sqrt(var > 0.0 ? var : 0.0) : NAN;
       ent_mean = a * (0.5 + static_cast<double>(kHalfLog2Pi)) + s;
     }
-    const double lp_mean = t[1] / Bn;
-    double lp_var = (t[2] - t[1] * lp_mean) / (Bn - 1.0);
     p.info[0] = static_cast<float>(t[0] / Bn - p.ent_coef * ent_mean);  // policy_loss
-    p.info[1] = static_cast<float>(lp_mean);
-    p.info[2] = static_cast<float>(sqrt(lp_var > 0.0 ? lp_var : 0.0));
-    p.info[3] = static_cast<float>(t[3]);
-    p.info[4] = static_cast<float>(t[4]);
-    p.info[5] = static_cast<float>(t[5]);
-    p.info[6] = static_cast<float>(t[6]);
     p.info[7] = static_cast<float>(ls_mean);
     p.info[8] = static_cast<float>(ls_std);
     p.info[9] = static_cast<float>(ls_max);
     p.info[10] = static_cast<float>(ls_min);
     p.info[11] = static_cast<float>(ent_mean);
+  } else if (threadIdx.x == 32) {
+    const double lp_mean = t[1] / Bn;
+    const double lp_var = (t[2] - t[1] * lp_mean) / (Bn - 1.0);
+    p.info[1] = static_cast<float>(lp_mean);
+    p.info[2] = static_cast<float>(sqrt(lp_var > 0.0 ? lp_var : 0.0));
+  } else if (threadIdx.x == 64) {
+    p.info[3] = static_cast<float>(t[3]);
+    p.info[4] = static_cast<float>(t[4]);
+    p.info[5] = static_cast<float>(t[5]);
+    p.info[6] = static_cast<float>(t[6]);
     p.info[12] = static_cast<float>(t[11] / Bn);
-    if (!p.ls_stride)
-      for (int j = 0; j < a; ++j) {
-        bool pass;
-        clamped_ls(p, p.log_std[j], &pass);
-        p.g_log_std[j] = pass ? static_cast<float>(t[kActorFixed + j]) - p.ent_coef : 0.f;
-      }
-    *p.ticket = 0u;
+  } else if (threadIdx.x >= 96 && threadIdx.x < 96 + a && !p.ls_stride) {
+    const int j = threadIdx.x - 96;
+    bool pass;
+    clamped_ls(p, p.log_std[j], &pass);
+    p.g_log_std[j] = pass ? static_cast<float>(t[kActorFixed + j]) - p.ent_coef : 0.f;
   }
+  if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
 // ------------------------------------------------------------------------------------ critic
