@@ -293,6 +293,19 @@ int trl_skinny_act_wgrad(const float* G, const float* Y, const float* X, float* 
 int64_t trl_skinny_dgrad_act_scratch_floats(int64_t M, int H);
 int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* Y, float* gz, float* db, int64_t M, int H,
                            int N, int act, float* scratch, void* stream);
+/* First stages alone + ONE launch for all the second stages of a backward pass.  The *_partial entry points run only the
+ * pass over the (M x H) matrix and leave the per-CTA slabs in `scratch` (one scratch buffer per pending job, untouched
+ * until the reduce); trl_skinny_reduce_jobs finishes up to 8 jobs in one launch.  kind: 0 = trl_skinny_tn (colsum NULL or
+ * (K)), 1 = trl_skinny_act_wgrad (colsum = db (H)), 2 = trl_skinny_n_dgrad_act (colsum = db (H); out / K unused). */
+int trl_skinny_tn_partial(const float* A, const float* B, int64_t M, int H, int K, int want_colsum, float* scratch,
+                          void* stream);
+int trl_skinny_act_wgrad_partial(const float* G, const float* Y, const float* X, int64_t M, int H, int K, int act,
+                                 float* scratch, void* stream);
+int trl_skinny_n_dgrad_act_partial(const float* G, const float* W, const float* Y, float* gz, int64_t M, int H, int N,
+                                   int act, float* scratch, void* stream);
+int trl_skinny_reduce_jobs(int njobs, const int* kind, const float* const* scratch, float* const* out,
+                           float* const* colsum, const int64_t* M, const int* H, const int* K, const int* out_transposed,
+                           void* stream);
 
 /* ---- K1 for BASELINE config 4: synthetic Atari-shaped pixel env, obs (N,4,84,84) uint8, 6 actions (defined in
  * oracle/synth_atari.py; the reference only wraps real ALE games, env/atari_wrapper.py).  latent: (N,5) int32. */

@@ -169,7 +169,7 @@ class A2C(OnRLAlgo):
         """One minibatch update reading its row indices at device position `upd`.  Layer gradients go straight into
         the flat gradient buffer (networks.fused.direct_grad): every parameter gets exactly one contribution per
         minibatch and the optimizer step left the buffer zeroed."""
-        with fused.direct_grad():
+        with fused.direct_grad(), fused.deferred_reduces():
             st, rb = self._mb_state, self.replay_buffer
             batch = rb.gather_rows(st["perm"], st["keys"], pos_ptr=st["upd"], rows=st["b"])
             info = st["info"][0]
@@ -187,6 +187,7 @@ class A2C(OnRLAlgo):
             else:
                 self._critic_step(batch, info)
                 self._actor_step(batch, info)
+            fused.flush_reduces()              # the slab sums of both networks' skinny gradients, one launch
             scale, fused_norm = 1.0, False
             if self.dist is not None:
                 scale, fused_norm = self.dist.reduce_grads(self.opt, self._step_mask())   # exchange + norms, one kernel

@@ -260,14 +260,11 @@ __global__ void __launch_bounds__(256, 2) skinny_tn_kernel(const float* __restri
 // the other network's kernels still hold most of every SM.
 constexpr int kRedGroups = 32;
 constexpr int kRedElems = 8;
-__global__ void __launch_bounds__(kRedElems * kRedGroups) skinny_tn_reduce_kernel(const float* __restrict__ partial,
-                                                                                 float* __restrict__ Out,
-                                                                                 float* __restrict__ colsum, int n_cs,
-                                                                                 int nslab, int H, int K,
-                                                                                 int out_transposed) {
-  __shared__ float red[kRedGroups][kRedElems + 1];
+__device__ __forceinline__ void tn_reduce_block(const float* __restrict__ partial, float* __restrict__ Out,
+                                                float* __restrict__ colsum, int n_cs, int nslab, int H, int K,
+                                                int out_transposed, int block, float (*red)[kRedElems + 1]) {
   const int el = threadIdx.x & (kRedElems - 1), g = threadIdx.x / kRedElems;
-  const int e = blockIdx.x * kRedElems + el;
+  const int e = block * kRedElems + el;
   const int n_main = K * H;
   const int n_all = n_main + n_cs;                       // n_cs trailing entries of row K go to colsum[]
   const long long stride = static_cast<long long>(K + 1) * H;
@@ -298,6 +295,35 @@ __global__ void __launch_bounds__(kRedElems * kRedGroups) skinny_tn_reduce_kerne
       colsum[e - n_main] = s;
     }
   }
+}
+
+__global__ void __launch_bounds__(kRedElems * kRedGroups) skinny_tn_reduce_kernel(const float* __restrict__ partial,
+                                                                                 float* __restrict__ Out,
+                                                                                 float* __restrict__ colsum, int n_cs,
+                                                                                 int nslab, int H, int K,
+                                                                                 int out_transposed) {
+  __shared__ float red[kRedGroups][kRedElems + 1];
+  tn_reduce_block(partial, Out, colsum, n_cs, nslab, H, K, out_transposed, blockIdx.x, red);
+}
+
+// Several second stages in ONE launch (the slab sums of a whole backward pass: two first-layer, two output-layer weight
+// gradients and two bias gradients per PPO minibatch are six launches of a few microseconds of latency each otherwise).
+constexpr int kMaxRedJobs = 8;
+struct ReduceJobs {
+  const float* partial[kMaxRedJobs];
+  float* out[kMaxRedJobs];
+  float* colsum[kMaxRedJobs];
+  int n_cs[kMaxRedJobs], nslab[kMaxRedJobs], H[kMaxRedJobs], K[kMaxRedJobs], out_t[kMaxRedJobs];
+  int cta_begin[kMaxRedJobs + 1];
+  int njobs;
+};
+__global__ void __launch_bounds__(kRedElems * kRedGroups) skinny_reduce_jobs_kernel(const ReduceJobs q) {
+  __shared__ float red[kRedGroups][kRedElems + 1];
+  int j = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxRedJobs; ++i) j += (i < q.njobs && static_cast<int>(blockIdx.x) >= q.cta_begin[i]) ? 1 : 0;
+  tn_reduce_block(q.partial[j], q.out[j], q.colsum[j], q.n_cs[j], q.nslab[j], q.H[j], q.K[j], q.out_t[j],
+                  static_cast<int>(blockIdx.x) - q.cta_begin[j], red);
 }
 
 // ------------------------------------------------------------------------------------------------- skinny_n_fwd
@@ -495,7 +521,7 @@ TRL_API int64_t trl_skinny_tn_scratch_floats(int64_t M, int H, int K) {
 
 static int launch_skinny_tn(const float* A, const float* Yact, const float* B, float* Out, float* colsum, int64_t M,
                             int H, int K, int out_transposed, int act, bool fused_act, float* scratch, void* stream,
-                            const char* who) {
+                            const char* who, bool defer = false) {
   using namespace trl;
   TRL_REQUIRE(M >= 1 && K >= 1 && K <= 24 && H >= 32 && H % 32 == 0 && H <= 256,
               "%s: need 1<=K<=24, H%%32==0, H<=256 (K=%d H=%d)", who, K, H);
@@ -520,7 +546,7 @@ static int launch_skinny_tn(const float* A, const float* Yact, const float* B, f
   }
 #undef TRL_TN
   int rc = check_launch("skinny_tn_kernel");
-  if (rc != TRL_OK) return rc;
+  if (rc != TRL_OK || defer) return rc;
   const int n_cs = colsum ? (fused_act ? H : K) : 0;
   const int n_all = K * H + n_cs;
   skinny_tn_reduce_kernel<<<ceil_div(n_all, kRedElems), kRedElems * kRedGroups, 0, st>>>(scratch, Out, colsum, n_cs, nslab, H, K, out_transposed);
@@ -588,12 +614,12 @@ TRL_API int64_t trl_skinny_dgrad_act_scratch_floats(int64_t M, int H) {
 
 // Output-layer dgrad fused with the previous layer's activation backward:
 //   gz (M,H) = (G (M,N) . W (N,H)) * act'(Y (M,H)),   db (H) = colsum(gz).   scratch: ..._scratch_floats(M,H) floats.
-TRL_API int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* Y, float* gz, float* db, int64_t M,
-                                   int H, int N, int act, float* scratch, void* stream) {
+static int launch_n_dgrad_act(const float* G, const float* W, const float* Y, float* gz, float* db, int64_t M, int H, int N,
+                              int act, float* scratch, void* stream, bool defer) {
   using namespace trl;
   TRL_REQUIRE(M >= 1 && N >= 1 && N <= 8 && H >= 4 && H % 4 == 0 && H <= 1024,
               "trl_skinny_n_dgrad_act: need N<=8, H%%4==0, H<=1024");
-  TRL_REQUIRE(G && W && Y && gz && db && scratch, "trl_skinny_n_dgrad_act: null pointer");
+  TRL_REQUIRE(G && W && Y && gz && (db || defer) && scratch, "trl_skinny_n_dgrad_act: null pointer");
   TRL_REQUIRE(act >= 0 && act <= 2, "trl_skinny_n_dgrad_act: unknown activation %d", act);
   TRL_REQUIRE(aligned16(W) && aligned16(gz) && aligned16(Y), "trl_skinny_n_dgrad_act: W/Y/gz must be 16-byte aligned");
   const int rows = sk_rows_per_cta(M);
@@ -601,8 +627,72 @@ TRL_API int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   skinny_n_dgrad_kernel<true><<<nslab, 256, sizeof(float) * rows * 8, st>>>(G, W, Y, act, gz, scratch, M, H, N, rows);
   int rc = check_launch("skinny_n_dgrad_kernel");
-  if (rc != TRL_OK) return rc;
+  if (rc != TRL_OK || defer) return rc;
   // column sums: partial [nslab][H] viewed as a K = 0 "tn" partial (stride H, all H entries are colsum entries)
   skinny_tn_reduce_kernel<<<ceil_div(H, kRedElems), kRedElems * kRedGroups, 0, st>>>(scratch, db, db, H, nslab, H, 0, 0);
   return check_launch("skinny_tn_reduce_kernel");
+}
+
+TRL_API int trl_skinny_n_dgrad_act(const float* G, const float* W, const float* Y, float* gz, float* db, int64_t M,
+                                   int H, int N, int act, float* scratch, void* stream) {
+  return launch_n_dgrad_act(G, W, Y, gz, db, M, H, N, act, scratch, stream, false);
+}
+
+// ---- first stages alone + ONE launch for all the second stages of a backward pass -------------------------------------
+// The *_partial entry points run only the pass over the (M x H) matrix and leave the per-CTA slabs in `scratch` (which
+// must then stay untouched, one scratch buffer per pending job); trl_skinny_reduce_jobs finishes up to 8 such jobs in one
+// launch.  kind: 0 = trl_skinny_tn (colsum NULL or (K)), 1 = trl_skinny_act_wgrad (colsum = db (H)), 2 =
+// trl_skinny_n_dgrad_act (colsum = db (H); out / K / out_transposed unused).
+TRL_API int trl_skinny_tn_partial(const float* A, const float* B, int64_t M, int H, int K, int want_colsum, float* scratch,
+                                  void* stream) {
+  float dummy;
+  return launch_skinny_tn(A, nullptr, B, &dummy, want_colsum ? &dummy : nullptr, M, H, K, 0, 0, false, scratch, stream,
+                          "trl_skinny_tn_partial", true);
+}
+
+TRL_API int trl_skinny_act_wgrad_partial(const float* G, const float* Y, const float* X, int64_t M, int H, int K, int act,
+                                         float* scratch, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(Y, "trl_skinny_act_wgrad_partial: null pointer");
+  TRL_REQUIRE(act >= 0 && act <= 2, "trl_skinny_act_wgrad_partial: unknown activation %d", act);
+  float dummy;
+  return launch_skinny_tn(G, Y, X, &dummy, &dummy, M, H, K, 0, act, true, scratch, stream, "trl_skinny_act_wgrad_partial", true);
+}
+
+TRL_API int trl_skinny_n_dgrad_act_partial(const float* G, const float* W, const float* Y, float* gz, int64_t M, int H, int N,
+                                           int act, float* scratch, void* stream) {
+  return launch_n_dgrad_act(G, W, Y, gz, nullptr, M, H, N, act, scratch, stream, true);
+}
+
+TRL_API int trl_skinny_reduce_jobs(int njobs, const int* kind, const float* const* scratch, float* const* out,
+                                   float* const* colsum, const int64_t* M, const int* H, const int* K,
+                                   const int* out_transposed, void* stream) {
+  using namespace trl;
+  TRL_REQUIRE(njobs >= 0 && njobs <= kMaxRedJobs, "trl_skinny_reduce_jobs: njobs %d not in 0..%d", njobs, kMaxRedJobs);
+  if (njobs == 0) return TRL_OK;
+  TRL_REQUIRE(kind && scratch && out && colsum && M && H && K && out_transposed, "trl_skinny_reduce_jobs: null table");
+  ReduceJobs q;
+  int ctas = 0;
+  for (int j = 0; j < kMaxRedJobs; ++j) {
+    q.cta_begin[j] = ctas;
+    if (j >= njobs) { q.partial[j] = nullptr; q.out[j] = nullptr; q.colsum[j] = nullptr; q.n_cs[j] = q.nslab[j] = q.H[j] = q.K[j] = q.out_t[j] = 0; continue; }
+    TRL_REQUIRE(kind[j] >= 0 && kind[j] <= 2 && scratch[j] && M[j] >= 1 && H[j] >= 1, "trl_skinny_reduce_jobs: bad job %d", j);
+    const int rows = sk_rows_per_cta(M[j]);
+    q.partial[j] = scratch[j];
+    q.nslab[j] = static_cast<int>(ceil_div<long long>(M[j], rows));
+    q.H[j] = H[j];
+    if (kind[j] == 2) {
+      TRL_REQUIRE(colsum[j], "trl_skinny_reduce_jobs: job %d needs colsum", j);
+      q.out[j] = colsum[j]; q.colsum[j] = colsum[j]; q.K[j] = 0; q.n_cs[j] = H[j]; q.out_t[j] = 0;
+    } else {
+      TRL_REQUIRE(out[j] && K[j] >= 1 && K[j] <= 24 && (kind[j] == 0 || colsum[j]), "trl_skinny_reduce_jobs: bad job %d", j);
+      q.out[j] = out[j]; q.colsum[j] = colsum[j]; q.K[j] = K[j]; q.out_t[j] = out_transposed[j];
+      q.n_cs[j] = colsum[j] ? (kind[j] == 1 ? H[j] : K[j]) : 0;
+    }
+    ctas += ceil_div(q.K[j] * q.H[j] + q.n_cs[j], kRedElems);
+  }
+  q.cta_begin[kMaxRedJobs] = ctas;
+  q.njobs = njobs;
+  skinny_reduce_jobs_kernel<<<ctas, kRedElems * kRedGroups, 0, static_cast<cudaStream_t>(stream)>>>(q);
+  return check_launch("skinny_reduce_jobs_kernel");
 }

@@ -305,10 +305,78 @@ def _tn_scratch(M, H, K, device):
     return ws
 
 
-def skinny_tn(a, b, out=None, colsum=None, out_transposed=False):
+# ---- deferred second stages ---------------------------------------------------------------------------------------------
+# Every skinny weight / bias gradient is "per-CTA slabs, then a small kernel that sums the slabs".  Inside a
+# `deferred_reduces()` scope (the fused minibatch body, where gradients go straight into the flat buffer and nobody reads
+# them before the optimizer) only the first stages are launched; `flush_reduces()` sums the slabs of ALL pending jobs in
+# ONE launch (trl_skinny_reduce_jobs): six few-microsecond launches per PPO minibatch become one.
+_DEFER = None           # list of pending jobs while a scope is open (backward runs on autograd threads: module state)
+
+
+class deferred_reduces:
+    def __enter__(self):
+        global _DEFER
+        self._prev = _DEFER
+        _DEFER = []
+        return self
+
+    def __exit__(self, *exc):
+        global _DEFER
+        jobs, _DEFER = _DEFER, self._prev
+        if jobs and exc[0] is None:
+            raise RuntimeError("deferred_reduces: %d pending jobs; call flush_reduces() inside the scope" % len(jobs))
+        return False
+
+
+def _defer_scratch(kind, M, H, K, device):
+    """One scratch buffer per pending job (its slabs must survive until the flush): keyed by the job's position."""
+    slot = len(_DEFER)
+    key = ("defer", slot, kind, M, H, K, str(device))
+    ws = _TN_WS.get(key)
+    if ws is None:
+        lib = _lib.load()
+        n = int(lib.trl_skinny_dgrad_act_scratch_floats(M, H)) if kind == 2 else int(lib.trl_skinny_tn_scratch_floats(M, H, K))
+        ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=device)
+    return ws
+
+
+def flush_reduces():
+    """Second stages of every job recorded since the scope opened, on the current stream (which must already be ordered
+    after the streams the first stages ran on)."""
+    import ctypes
+    global _DEFER
+    jobs = _DEFER
+    if not jobs:
+        return
+    for i in range(0, len(jobs), 8):
+        part = jobs[i:i + 8]
+        n = len(part)
+        vp = ctypes.c_void_p
+        _lib.call("trl_skinny_reduce_jobs", n, (ctypes.c_int * n)(*[j[0] for j in part]),
+                  (vp * n)(*[j[1].data_ptr() for j in part]),
+                  (vp * n)(*[0 if j[2] is None else j[2].data_ptr() for j in part]),
+                  (vp * n)(*[0 if j[3] is None else j[3].data_ptr() for j in part]),
+                  (ctypes.c_int64 * n)(*[j[4] for j in part]), (ctypes.c_int * n)(*[j[5] for j in part]),
+                  (ctypes.c_int * n)(*[j[6] for j in part]), (ctypes.c_int * n)(*[j[7] for j in part]), ops._stream())
+    _DEFER = []
+
+
+def _can_defer(*outs):
+    """Deferral is only sound when every output is a slice of the flat gradient buffer (direct_grad): autograd would
+    otherwise accumulate a tensor that is not complete yet."""
+    return _DEFER is not None and all(o is not None for o in outs)
+
+
+def skinny_tn(a, b, out=None, colsum=None, out_transposed=False, may_defer=False):
     """out = a^T @ b for a (M,H), b (M,K<=32) [+ colsum = b.sum(0)]: csrc/skinny.cu, two deterministic stages."""
     M, H = a.shape
     K = b.shape[1]
+    if may_defer and _can_defer(out) and len(_DEFER) < 64:
+        ws = _defer_scratch(0, M, H, K, a.device)
+        _lib.call("trl_skinny_tn_partial", ops._chk(a, torch.float32, "a"), ops._chk(b, torch.float32, "b"), M, H, K,
+                  int(colsum is not None), ws.data_ptr(), ops._stream())
+        _DEFER.append((0, ws, out, colsum, M, H, K, int(bool(out_transposed))))
+        return out
     ws = _tn_scratch(M, H, K, a.device)
     if out is None:
         out = torch.empty((K, H) if out_transposed else (H, K), dtype=torch.float32, device=a.device)
@@ -369,6 +437,12 @@ class _LinearAct(torch.autograd.Function):
             # first layer (its input needs no gradient): dW and db straight from g and y in ONE pass over the
             # (M, H) matrices; the activation gradient gz is never written to memory
             dw = dw_out if dw_out is not None else torch.empty(H, K, dtype=torch.float32, device=y.device)
+            if _can_defer(dw_out, db_out):
+                ws = _defer_scratch(1, M, H, K, y.device)
+                _lib.call("trl_skinny_act_wgrad_partial", g.data_ptr(), y.data_ptr(), x.data_ptr(), M, H, K, ctx.act,
+                          ws.data_ptr(), ops._stream())
+                _DEFER.append((1, ws, dw, db, M, H, K, 0))
+                return None, None, None, None
             _lib.call("trl_skinny_act_wgrad", g.data_ptr(), y.data_ptr(), x.data_ptr(), dw.data_ptr(), db.data_ptr(),
                       M, H, K, ctx.act, _tn_scratch(M, H, K, y.device).data_ptr(), ops._stream())
             _lib.add_launches(1)
@@ -479,26 +553,33 @@ class _MLPTail(torch.autograd.Function):
         db2 = db2_out if db2_out is not None else torch.empty(H, dtype=torch.float32, device=dev)
         db3 = db3_out if db3_out is not None else torch.empty(N, dtype=torch.float32, device=dev)
         gz = torch.empty_like(y2)
-        key = ("dgrad_act", M, H, str(dev), _stream_key())
-        ws = _TN_WS.get(key)
-        if ws is None:
-            n = int(_lib.load().trl_skinny_dgrad_act_scratch_floats(M, H))
-            ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=dev)
-        _lib.call("trl_skinny_n_dgrad_act", g.data_ptr(), w3.data_ptr(), y2.data_ptr(), gz.data_ptr(), db2.data_ptr(),
-                  M, H, N, ctx.act, ws.data_ptr(), ops._stream())
-        _lib.add_launches(1)
+        if _can_defer(db2_out):
+            ws = _defer_scratch(2, M, H, 0, dev)
+            _lib.call("trl_skinny_n_dgrad_act_partial", g.data_ptr(), w3.data_ptr(), y2.data_ptr(), gz.data_ptr(), M, H, N,
+                      ctx.act, ws.data_ptr(), ops._stream())
+            _DEFER.append((2, ws, None, db2, M, H, 0, 0))
+        else:
+            key = ("dgrad_act", M, H, str(dev), _stream_key())
+            ws = _TN_WS.get(key)
+            if ws is None:
+                n = int(_lib.load().trl_skinny_dgrad_act_scratch_floats(M, H))
+                ws = _TN_WS[key] = torch.empty(n, dtype=torch.float32, device=dev)
+            _lib.call("trl_skinny_n_dgrad_act", g.data_ptr(), w3.data_ptr(), y2.data_ptr(), gz.data_ptr(), db2.data_ptr(),
+                      M, H, N, ctx.act, ws.data_ptr(), ops._stream())
+            _lib.add_launches(1)
         fk = _fork_here()
         if fk is not None and dw2_out is not None and dw3_out is not None:
             # the two weight gradients feed nothing but the optimizer: companion stream (see backward_fork)
             fk.side.wait_stream(fk.main)
             with torch.cuda.stream(fk.side):
-                dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)
+                dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True, may_defer=db3_out is not None)
                 dw2 = wgrad(gz, x, out=dw2_out)
             fk.keep += [gz, g, y2, x]
             fk.used = True
             dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
         else:
-            dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True)  # dW3 (N,H) = g^T y2, db3 = sum g
+            dw3 = skinny_tn(y2, g, out=dw3_out, colsum=db3, out_transposed=True,   # dW3 (N,H) = g^T y2, db3 = sum g
+                            may_defer=dw3_out is not None and db3_out is not None)
             dx = mm_dgrad(gz, w2) if ctx.needs_input_grad[0] else None
             dw2 = wgrad(gz, x, out=dw2_out)
         return (dx, None if dw2_out is not None else dw2, None if db2_out is not None else db2,

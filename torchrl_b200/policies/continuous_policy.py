@@ -152,7 +152,10 @@ class GuassianContPolicyBase:
 
     def act_only(self, x, eps=None, action_out=None, nan_flag=None):
         """Collector fast path: sampled action only (no entropy / dict), one launch after the MLP."""
-        mean, _, log_std = self.forward(x)
+        if hasattr(self, "mean_and_log_std"):
+            mean, log_std = self.mean_and_log_std(x)         # no exp(log_std) launch: the sampler works on log_std
+        else:
+            mean, _, log_std = self.forward(x)
         mean = mean if mean.is_contiguous() else mean.contiguous()
         ls = log_std if log_std.dim() == 1 else log_std.expand_as(mean).contiguous()
         rng = self._rng_state(mean.device)
@@ -209,6 +212,10 @@ class GuassianContPolicyBasicBias(networks.Net, GuassianContPolicyBase):
 
     def clamped_logstd(self):
         return torch.clamp(self.logstd, LOG_SIG_MIN, LOG_SIG_MAX)
+
+    def mean_and_log_std(self, x):
+        """forward() without the std = exp(log_std) tensor (callers that only sample)."""
+        return networks.Net.forward(self, x), torch.clamp(self.logstd, LOG_SIG_MIN, LOG_SIG_MAX)
 
     def forward(self, x):
         mean = networks.Net.forward(self, x)
