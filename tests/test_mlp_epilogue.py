@@ -215,3 +215,41 @@ def test_skinny_backward_is_deterministic():
         grads.append([p.grad.clone() for p in net.parameters()])
     for a, b in zip(*grads):
         assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("out", [1, 6])
+def test_deferred_slab_sums_equal_the_immediate_ones(out):
+    """Inside fused.deferred_reduces() (with direct_grad: gradients written straight into the flat buffer) the skinny
+    weight / bias gradients launch only their first stage; flush_reduces() sums all slabs in ONE launch
+    (trl_skinny_reduce_jobs).  Same kernels, same fold order: the gradients are bit-identical to the immediate route."""
+    import torch
+    import torch.nn as nn
+    import torchrl_b200.networks as networks
+    from torchrl_b200.flat import FlatAdam
+    from torchrl_b200.networks import fused
+    torch.manual_seed(out)
+    M = 16384
+    net = networks.Net(input_shape=17, output_shape=out, hidden_shapes=[256, 256], append_hidden_shapes=[],
+                       base_type=networks.MLPBase, activation_func=nn.Tanh).cuda()
+    opt = FlatAdam([net], lrs=[1e-3], eps=1e-5, max_norms=[0.5])
+    x = torch.randn(M, 17, device="cuda")
+    w = torch.randn(M, out, device="cuda")
+    with fused.presplit(), fused.direct_grad():
+        y = net(x)
+        torch.autograd.backward([y], [w])
+    immediate = opt.grad.clone()
+    assert float(immediate.abs().max()) > 0
+    opt.zero_grad()
+    with fused.presplit(), fused.direct_grad(), fused.deferred_reduces():
+        y = net(x)
+        torch.autograd.backward([y], [w])
+        n_jobs = len(fused._DEFER)
+        fused.flush_reduces()
+    assert n_jobs == 3                          # first-layer dW/db, output-layer dW/db, last hidden layer's db
+    assert torch.equal(opt.grad, immediate)
+    # leaving the scope with pending jobs is an error, not a silent loss of gradients
+    opt.zero_grad()
+    with pytest.raises(RuntimeError):
+        with fused.presplit(), fused.direct_grad(), fused.deferred_reduces():
+            torch.autograd.backward([net(x)], [w])
