@@ -3,6 +3,8 @@ include/torchrl_b200.h declares, and the product package never imports the oracl
 import os
 import re
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -57,3 +59,22 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     import pytest
     with pytest.raises(_lib.NativeLibraryError):
         _lib.load()
+
+
+def test_deferred_reduce_scope_is_strict():
+    """networks.fused.deferred_reduces(): pending slab-sum jobs must be flushed inside the scope (a silent drop would
+    lose gradients); an empty flush is a no-op and the scope restores the previous state.  Host logic only."""
+    from torchrl_b200.networks import fused
+    assert fused._DEFER is None
+    with fused.deferred_reduces():
+        assert fused._DEFER == []
+        fused.flush_reduces()                      # nothing recorded: no library call
+        with fused.deferred_reduces():             # nested scopes keep their own job lists
+            assert fused._DEFER == []
+        assert fused._DEFER == []
+    assert fused._DEFER is None
+    with pytest.raises(RuntimeError):
+        with fused.deferred_reduces():
+            fused._DEFER.append((0, None, None, None, 1, 32, 1, 0))
+    assert fused._DEFER is None
+    assert not fused._can_defer(object())          # outside a scope nothing is deferred

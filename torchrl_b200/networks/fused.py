@@ -6,7 +6,9 @@ Routing of one Linear layer (default matmul mode "tc3"):
     dgrad reading the weights N-major (no transpose), wgrad with both operands M/N-major and deterministic split-K.
     Inside a `presplit()` scope the weights come as pre-split TF32 planes kept current by the fused Adam / Polyak
     kernels (flat.FlatParams.hi / .lo); elsewhere the kernel splits them in shared memory.
-  * first layer (K = obs_dim <= 24) and output layer (<= 8 units): csrc/skinny.cu (memory-bound fp32 kernels).
+  * first layer (K = obs_dim <= 24) and output layer (<= 8 units): csrc/skinny.cu (fp32 kernels that stream one
+    (M x H) matrix each, weights in registers).  Their weight / bias gradients are "per-CTA slabs, then a slab sum";
+    inside `deferred_reduces()` (the fused minibatch body) only the first stages run and ONE launch sums all slabs.
   * anything else: cuBLAS fp32 SIMT + the fused bias/activation epilogues of csrc/mlp_epilogue.cu.
 Numerically every route is fp32 arithmetic (3xTF32: 2e-6 relative at K = 256); the bias gradient is a fixed-order
 two-level sum.
@@ -22,7 +24,8 @@ from .. import _lib, ops
 ACT_CODES = {nn.Tanh: 1, nn.ReLU: 2}
 _ENABLED = True
 # "tc3"   : 256-wide layers with >= _TC3_MIN_ROWS rows on the hand-written tcgen05 3xTF32 kernel
-#           (csrc/gemm_tf32x3.cu, fp32-faithful), everything else cuBLAS fp32 SIMT            [default]
+#           (csrc/gemm_pair.cu, fp32-faithful), skinny first / output layers on csrc/skinny.cu,
+#           everything else cuBLAS fp32 SIMT                                                   [default]
 # "fp32"  : cuBLAS fp32 SIMT sgemm everywhere
 # "tf32x3": error-compensated TF32 through three cuBLAS GEMMs (kept for comparison; no faster than fp32)
 _MATMUL_MODE = "tc3"
@@ -284,10 +287,10 @@ _TN_WS = {}
 
 def set_skinny(flag):
     """Route the first (K = obs_dim <= 24) and output (N <= 8) Linear layers through csrc/skinny.cu (default on).
-    Measured on B200 at M = 16384, cold L2, including ~7 us of launch/event overhead (scripts/skinny_bench.py,
-    profiles/skinny_bench_r1.txt): k_fwd 18.5 us vs cuBLAS + epilogue 27.6; n_fwd 12.3 vs 23.2; n_dgrad 10.2 vs
-    12.3; output-layer wgrad + bias gradient 21.5 vs 35.9; first-layer wgrad 23.5 vs 23.6.  `set_skinny(False)`
-    restores cuBLAS for these layers."""
+    Measured on B200 at M = 16384, warm L2, launch gap included (scripts/skinny_probe.py, profiles/skinny_probe_r2.txt):
+    k_fwd 8.3 us (cuBLAS + epilogue: 27.6 cold), n_fwd 4.9 / 3.1 us (N = 6 / 1), output-layer dgrad fused with the
+    activation backward + bias gradient 9.2, output-layer wgrad + bias gradient 8.4, first-layer wgrad + bias gradient
+    12.2.  `set_skinny(False)` restores cuBLAS for these layers."""
     global _SKINNY
     _SKINNY = bool(flag)
 
