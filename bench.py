@@ -53,7 +53,7 @@ def parse():
     ap.add_argument("--skip-secondary", action="store_true",
                     help="skip the secondary measurements (BASELINE configs[0], [2], [3] and the desynchronised-episode PPO)")
     ap.add_argument("--cpu-procs", type=int, default=0, help="env worker processes of the CPU arm (0 = auto)")
-    ap.add_argument("--cpu-budget-s", type=float, default=900.0,
+    ap.add_argument("--cpu-budget-s", type=float, default=600.0,
                     help="wall-clock budget of the CPU arm; whole epochs are dropped (never shortened) beyond it")
     ap.add_argument("--matmul", default="tc3", choices=["fp32", "tf32x3", "tc3"],
                     help="MLP GEMM path: tc3 = hand-written tcgen05 3xTF32 kernel on the 256-wide layers (default), fp32 = cuBLAS SIMT everywhere, tf32x3 = 3 cuBLAS TF32 GEMMs")
@@ -230,13 +230,14 @@ class CpuPipeline:
     synthetic gym env of oracle/synth_env.py.  `kind == "port"`: oracle/ref_port.py (pinned bit-for-bit to the
     reference by tests/test_oracle_vs_reference.py) -- only when no copy of the reference is present."""
 
-    def __init__(self, env_nums, proc_nums, threads, seed=0):
+    def __init__(self, env_nums, proc_nums, threads, seed=0, horizon=HORIZON):
         import numpy as np
         import torch
         from oracle import reference_loader
         torch.set_num_threads(threads)
-        self.env_nums, self.proc_nums, self.threads = env_nums, proc_nums, threads
-        self.frames = HORIZON * env_nums
+        assert horizon % BATCH_ROWS == 0
+        self.env_nums, self.proc_nums, self.threads, self.horizon = env_nums, proc_nums, threads, horizon
+        self.frames = horizon * env_nums
         if reference_loader.available():
             self.kind = "reference"
             reference_loader.load()
@@ -256,13 +257,13 @@ class CpuPipeline:
             env.seed(seed)
             torch.manual_seed(seed)
             np.random.seed(seed)
-            buf = OnPolicyReplayBuffer(env_nums=env_nums, max_replay_buffer_size=HORIZON * env_nums, time_limit_filter=True)
+            buf = OnPolicyReplayBuffer(env_nums=env_nums, max_replay_buffer_size=horizon * env_nums, time_limit_filter=True)
             net = dict(hidden_shapes=list(HIDDEN), append_hidden_shapes=[], base_type=networks.MLPBase,
                        activation_func=torch.nn.Tanh)
             pf = policies.GuassianContPolicyBasicBias(input_shape=OBS_DIM, output_shape=ACT_DIM, tanh_action=True, **net)
             vf = networks.Net(input_shape=(OBS_DIM,), output_shape=1, **net)
             col = VecOnPolicyCollector(vf, env=env, eval_env=eval_env, pf=pf, replay_buffer=buf, device="cpu",
-                                       train_render=False, epoch_frames=HORIZON * env_nums, max_episode_frames=999,
+                                       train_render=False, epoch_frames=horizon * env_nums, max_episode_frames=999,
                                        eval_episodes=1)
             self._tmp = tempfile.mkdtemp(prefix="bench_ref_")
             agent = PPO(pf=pf, vf=vf, plr=3e-4, vlr=3e-4, clip_para=0.2, opt_epochs=OPT_EPOCHS, tau=0.95, shuffle=True,
@@ -273,7 +274,7 @@ class CpuPipeline:
         else:
             self.kind = "port"
             from oracle import ref_port
-            env, col, agent = ref_port.build_ppo(env_id=ENV_ID, env_nums=env_nums, proc_nums=proc_nums, horizon=HORIZON,
+            env, col, agent = ref_port.build_ppo(env_id=ENV_ID, env_nums=env_nums, proc_nums=proc_nums, horizon=horizon,
                                                  hidden=HIDDEN, batch_rows=BATCH_ROWS, opt_epochs=OPT_EPOCHS, seed=seed)
             self.env, self.eval_env, self.col, self.agent = env, None, col, agent
         self.epochs_done = 0
@@ -298,11 +299,16 @@ class CpuPipeline:
                 pass
 
     def describe(self):
-        return ("%s: whole epochs timed end to end, each = %d vec-env steps x %d envs over %d env worker processes "
-                "(SubProcVecEnv) + Python GAE + %d PPO minibatches of %d samples on %d torch threads"
-                % ("unmodified reference classes (oracle/_ref)" if self.kind == "reference" else "oracle/ref_port.py",
-                   HORIZON, self.env_nums, self.proc_nums, OPT_EPOCHS * (HORIZON // BATCH_ROWS),
-                   BATCH_ROWS * self.env_nums, self.threads))
+        s = ("%s: whole epochs timed end to end, each = %d vec-env steps x %d envs over %d env worker processes "
+             "(SubProcVecEnv) + Python GAE + %d PPO minibatches of %d samples on %d torch threads"
+             % ("unmodified reference classes (oracle/_ref)" if self.kind == "reference" else "oracle/ref_port.py",
+                self.horizon, self.env_nums, self.proc_nums, OPT_EPOCHS * (self.horizon // BATCH_ROWS),
+                BATCH_ROWS * self.env_nums, self.threads))
+        if self.horizon != HORIZON:
+            s += ("; BOUNDED SAMPLE: horizon %d instead of %d -- same env count, same minibatch size, same work per "
+                  "collector step and per minibatch, %dx fewer of both per epoch, so env-steps/s is unchanged while an "
+                  "epoch stays at ~1 GPU's worth of CPU work" % (self.horizon, HORIZON, HORIZON // self.horizon))
+        return s
 
 
 def auto_procs(env_nums, want=0):
@@ -350,7 +356,12 @@ def run_reference(args):
     procs, cores = auto_procs(env_nums, args.cpu_procs)
     threads = best_torch_threads(cores, BATCH_ROWS * env_nums)
     t_start = time.perf_counter()
-    pipe = CpuPipeline(env_nums, procs, threads)
+    # several GPUs' worth of envs: a whole 128-step epoch of the CPU pipeline would take world x ~35 s, and W + K of them
+    # far more than "a few minutes"; the horizon of the timed epochs shrinks with the world size instead (see describe())
+    horizon = HORIZON
+    while horizon * world > HORIZON and horizon // 2 >= 4 * BATCH_ROWS:
+        horizon //= 2
+    pipe = CpuPipeline(env_nums, procs, threads, horizon=horizon)
     try:
         warm, timed, parts = 0, [], []
         for i in range(args.warmup):
