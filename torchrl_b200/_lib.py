@@ -171,7 +171,8 @@ def add_launches(n):
 
 
 def call(name, *args):
-    """Invoke a kernel-launching entry point (each launches exactly one kernel) and raise on error."""
+    """Invoke a kernel-launching entry point and raise on error.  Counted as one launch (a few entry points launch a
+    second, small kernel: the count is a lower bound of the kernels launched)."""
     global _LAUNCHES
     lib = load()
     rc = getattr(lib, name)(*args)
